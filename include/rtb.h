@@ -1,0 +1,210 @@
+/* rtb.h — C ABI of the B200 ray-tracing backend ("rtb") that sits behind Scene::render().
+ *
+ * The reference (holoskii/Rendering) has no FFI: its boundary is the C++ member function
+ * `void Scene::render()` (reference include/scene.h:91, src/scene.cpp:595-657), which runs
+ * launchWorkers (scene.cpp:470-506) and launchSSAA (scene.cpp:542-593) over a loaded Scene and
+ * hands a `Vec3f frameBuffer[h*w]` to saveImage (src/util.cpp:15-76).  This header is the thin
+ * `extern "C"` surface a maintainer binds instead: plain pointers and sizes, no C++ or torch types.
+ *
+ *   host side  (librtb_host.so, dependency-free C++17):  rtb_scene_load / rtb_scene_view / ...
+ *       replaces Scene::loadScene (scene.cpp:62-334), Mesh::loadOBJ + AccelerationStructure::setup
+ *       (objects.cpp:177-394, 470-526) and flattens the result into the POD `RtbScene` below.
+ *   device side (librtb_cuda.so, CUDA sm_100a):            rtb_create / rtb_render / rtb_destroy
+ *       replaces launchWorkers + launchSSAA, i.e. everything between "Scene is loaded" and
+ *       "frameBuffer is full".  There is NO CPU fallback: every entry point fails with
+ *       RTB_ERR_CUDA when no device is usable.
+ *
+ * All arrays are host pointers owned by the caller for the duration of rtb_create(); the library
+ * copies what it needs to device memory.  Floats are IEEE-754 binary32.
+ */
+#ifndef RTB_H
+#define RTB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB_ABI_VERSION 1
+
+/* ---- status codes (reference: LOG_ERROR() prints and exit(-1)s, include/util.h:13-19) ---- */
+#define RTB_OK             0
+#define RTB_ERR_ARG       -1   /* null / inconsistent argument                                   */
+#define RTB_ERR_IO        -2   /* file missing / unreadable (scene, obj, bmp)                    */
+#define RTB_ERR_PARSE     -3   /* malformed .scene / .obj (reference would LOG_ERROR)            */
+#define RTB_ERR_CUDA      -4   /* CUDA runtime error, or no device: no CPU fallback exists       */
+#define RTB_ERR_NOMEM     -5
+#define RTB_ERR_UNSUPPORTED -6
+
+/* ---- enums mirror the reference's (include/objects.h:17-18, include/lights.h:11) ---- */
+enum { RTB_OBJ_SPHERE = 1, RTB_OBJ_PLANE = 2, RTB_OBJ_MESH = 3 };
+enum { RTB_MAT_DIFFUSE = 0, RTB_MAT_REFLECTIVE = 1, RTB_MAT_TRANSPARENT = 2, RTB_MAT_PHONG = 3 };
+enum { RTB_LIGHT_DISTANT = 1, RTB_LIGHT_POINT = 2, RTB_LIGHT_AREA = 3 };
+
+/* process-global switches of the reference's `namespace options` (include/options.h:26-36) */
+#define RTB_FLAG_BACKFACE_CULLING  (1u << 0)   /* options::useBackfaceCulling (objects.cpp:75)   */
+#define RTB_FLAG_USE_AC            (1u << 1)   /* options::useAC (objects.cpp:536)               */
+#define RTB_FLAG_USE_SKYBOX        (1u << 2)   /* options::useSkybox (scene.cpp:383)             */
+#define RTB_FLAG_SHOW_NORMALS      (1u << 3)   /* options::showNormals (scene.cpp:771)           */
+#define RTB_FLAG_ENABLE_SSAA       (1u << 4)   /* options::enableSSAA (scene.cpp:604)            */
+
+/* Camera (include/scene.h:51-65).  rMatrix = mz*my*mx built on the host with sinf/cosf exactly as
+ * Camera::getRay does (scene.cpp:24-48), row-major 4x4, applied as row-vector x matrix.
+ * scale = tanf(fov*0.5f/180.0f*(float)M_PI), aspect = width/(float)height (scene.cpp:447-448).   */
+typedef struct RtbCamera {
+    float pos[3];
+    float rMatrix[16];
+    float scale;
+    float aspect;
+} RtbCamera;
+
+/* One scene object (include/objects.h:24-46, 165-191).  `mesh` indexes RtbScene.meshes for
+ * RTB_OBJ_MESH, else -1.  Sphere: pos + r2 (= powf(r,2), scene.cpp:294).  Plane: pos + normal
+ * (NOT normalised when it comes from the scene file, scene.cpp:299-301).                          */
+typedef struct RtbObject {
+    int32_t type;
+    int32_t material;
+    float   color[3];
+    float   ior;
+    float   ambient, diffuse, specular, nSpecular;
+    float   pos[3];
+    float   r2;
+    float   normal[3];
+    int32_t mesh;
+} RtbObject;
+
+/* One light (include/lights.h:19-73).  v = dir (distant, un-normalised from file) or pos (point /
+ * area centre).  Area lights: sample points are precomputed on the host exactly as
+ * AreaLight::setPoints (lights.cpp:46-63) and stored in RtbScene.areaPoints[pointOffset ...].     */
+typedef struct RtbLight {
+    int32_t type;
+    float   color[3];
+    float   intensity;
+    float   v[3];
+    int32_t pointOffset;
+    int32_t pointCount;
+} RtbLight;
+
+/* Node of the reference's per-mesh split tree (include/objects.h:128-163), DFS pre-order:
+ * the left child of inner node k is k+1, `right` is the right child's index; `right < 0` marks a
+ * leaf whose triangle references are refs[firstRef .. firstRef+refCount).  Leaves are numbered in
+ * the reference's traversal order (left before right, objects.cpp:601-619) so a reference slot
+ * index orders exact-t ties the way the recursive strict `<` does.                                 */
+typedef struct RtbNode {
+    float   lo[3];
+    float   hi[3];
+    int32_t right;
+    int32_t firstRef;
+    int32_t refCount;
+    int32_t depth;
+} RtbNode;
+
+/* 8-bit RGB image as loadBMP leaves it (util.cpp:78-113): 3 bytes/texel, R,G,B order (after the
+ * reference's B<->R swap), row 0 = first row in the file (BMP bottom row), no padding.            */
+typedef struct RtbImage {
+    const uint8_t* rgb;
+    int32_t width, height;
+} RtbImage;
+
+/* One triangle mesh (include/objects.h:69-121): SoA over triangles, in .obj face order.           */
+typedef struct RtbMesh {
+    int32_t nTris, nNodes, nRefs;
+    const float*   pos;       /* nTris*9  : a.xyz b.xyz c.xyz (world space, objects.cpp:306-320)   */
+    const float*   nrm;       /* nTris*9  : n_a n_b n_c                                            */
+    const float*   uv;        /* nTris*6  : t_a t_b t_c                                            */
+    const float*   tan;       /* nTris*6  : tangent.xyz bitangent.xyz (objects.cpp:43-55)          */
+    const RtbNode* nodes;     /* nNodes                                                            */
+    const int32_t* refs;      /* nRefs triangle indices, leaf by leaf                              */
+    RtbImage diffuseMap, normalMap, specularMap;   /* rgb == NULL when not loaded                  */
+} RtbMesh;
+
+typedef struct RtbScene {
+    int32_t   abiVersion;          /* RTB_ABI_VERSION                                              */
+    int32_t   width, height;       /* Options::width/height (include/options.h:12)                 */
+    float     bias;                /* Options::bias                                                */
+    int32_t   maxRayDepth;         /* Options::maxRayDepth                                         */
+    float     backgroundColor[3];
+    uint32_t  flags;               /* RTB_FLAG_*                                                   */
+    RtbCamera camera;
+    int32_t   nObjects, nLights, nMeshes, nAreaPoints;
+    const RtbObject* objects;
+    const RtbLight*  lights;
+    const RtbMesh*   meshes;
+    const float*     areaPoints;   /* nAreaPoints*3                                                */
+    RtbImage  skybox[6];           /* left,front,right,back,top,bottom (scene.cpp:336-360)         */
+} RtbScene;
+
+/* Work counters of one rtb_render call (64-bit: the reference's are int and wrap, stats.h:11-16). */
+typedef struct RtbStats {
+    uint64_t rays;          /* Render::trace invocations: primary + secondary + shadow + SSAA     */
+    uint64_t primaryRays, secondaryRays, shadowRays, ssaaPixels;
+    uint64_t boxTests;      /* only filled when the handle was created with RTB_CREATE_COUNTERS    */
+    uint64_t triTests;
+    uint32_t kernelLaunches;
+    uint32_t levels;
+    float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */
+} RtbStats;
+
+typedef struct RtbHandle RtbHandle;
+typedef struct RtbHostScene RtbHostScene;
+
+/* ===================== host side: librtb_host.so ===================== */
+
+/* Parse a .scene file the way Scene::loadScene does (scene.cpp:62-334), load meshes/textures,
+ * build each mesh's tree bit-for-bit like AccelerationStructure::setup (objects.cpp:470-526) and
+ * flatten.  Relative asset paths are tried against the cwd first (reference behaviour), then
+ * against the directory of the scene file.                                                         */
+int  rtb_scene_load(const char* scenePath, RtbHostScene** out);
+/* Same, from scene text in memory (assetDir resolves relative paths; may be NULL).                 */
+int  rtb_scene_parse(const char* sceneText, const char* assetDir, RtbHostScene** out);
+const RtbScene* rtb_scene_view(const RtbHostScene* hs);
+const char*     rtb_scene_image_name(const RtbHostScene* hs);
+void rtb_scene_free(RtbHostScene* hs);
+/* Per-mesh tree statistics {nodes, leaves, refs, maxLeaf, maxDepth, trisOutsideRoot}.              */
+int  rtb_scene_tree_stats(const RtbHostScene* hs, int mesh, int64_t out[6]);
+/* saveImage contract (util.cpp:15-76) with the well-defined quantisation (uint8)(clamp(v)*255).    */
+int  rtb_save_bmp(const char* path, const float* fb, int width, int height);
+const char* rtb_host_last_error(void);
+
+/* ===================== device side: librtb_cuda.so ===================== */
+
+#define RTB_CREATE_DEFAULT   0u
+#define RTB_CREATE_COUNTERS  (1u << 0)   /* count box / triangle tests (slower; parity of work)   */
+#define RTB_CREATE_EXACT_WALK (1u << 1)  /* traverse exactly like objects.cpp:587-631 (no culling) */
+
+/* Upload a flattened scene to `device` and build the device acceleration data.                     */
+int  rtb_create(const RtbScene* scene, int device, uint32_t createFlags, RtbHandle** out);
+
+/* Render rows [y0,y1) of the frame: pass 1 (launchWorkers) + Sobel + SSAA (launchSSAA), with the
+ * reference's quirks (last row/column black, pixel centre x+1.0, Sobel over unclamped floats).
+ * `fb` receives (y1-y0)*width*3 floats, row y0 first; it is a HOST pointer (copied back inside the
+ * call) when fbOnDevice == 0, else a device pointer on the handle's device.  `pass1` (optional,
+ * same shape and placement) receives the frame before SSAA.  `stream` is a cudaStream_t (NULL =
+ * the handle's own stream).  For multi-GPU strips use rtb_render_strips.                           */
+int  rtb_render(RtbHandle* h, int y0, int y1, float* fb, float* pass1, int fbOnDevice,
+                void* stream, RtbStats* stats);
+
+/* Render the rows owned by `rank` under a cyclic strip partition: strip s (stripRows rows) belongs
+ * to rank s % worldSize.  Output is compact: owned rows in ascending order; returns their count in
+ * *nRowsOut.  One halo row either side of every strip is rendered locally for the Sobel window.    */
+int  rtb_render_strips(RtbHandle* h, int stripRows, int rank, int worldSize, float* fb,
+                       int fbOnDevice, void* stream, int* nRowsOut, RtbStats* stats);
+/* Number of rows rank owns under that partition (for sizing buffers).                              */
+int  rtb_strip_rows_owned(int height, int stripRows, int rank, int worldSize);
+
+/* Closest-hit query on caller-supplied rays (orig.xyz dir.xyz per ray): the device equivalent of
+ * Render::trace (scene.cpp:724-756).  out: per ray {t,u,v} floats and {object,tri} ints (-1 miss). */
+int  rtb_trace(RtbHandle* h, const float* rays, int nRays, float* tuv, int32_t* objTri);
+/* Render::castRay (scene.cpp:758-946) on caller-supplied rays; out rgb per ray.                    */
+int  rtb_cast(RtbHandle* h, const float* rays, int nRays, float* rgb);
+
+int  rtb_device_of(const RtbHandle* h);
+void rtb_destroy(RtbHandle* h);
+const char* rtb_last_error(void);
+int  rtb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB_H */
