@@ -1,0 +1,432 @@
+// rt_device.cuh — per-ray arithmetic of the CUDA backend.
+//
+// Every function here is the device-side statement of one reference routine (cited per function).
+// The float pipeline is reproduced operation by operation: sums associate left to right, nothing
+// is contracted to FMA (the library is built with -fmad=false), divisions and square roots are the
+// IEEE-rounded ones, `normalize` goes through double exactly like the reference's unqualified
+// sqrt() does (include/geometry.h:99-112), comparisons keep their NaN behaviour.
+//
+// The functions are __host__ __device__ so tests/ can also compile this header with g++ and check
+// the arithmetic on the CPU box (tests/shim); the product only ever calls them from kernels.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define RT_HD __host__ __device__ __forceinline__
+#else
+#define RT_HD inline
+#endif
+
+namespace rt {
+
+struct V3 { float x, y, z; };
+struct V2 { float x, y; };
+
+RT_HD V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_HD V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_HD V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+RT_HD V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_HD V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+RT_HD V3 operator/(V3 a, float s) { return mk(a.x / s, a.y / s, a.z / s); }
+RT_HD float dot(V3 a, V3 b) { float s = a.x * b.x; s = s + a.y * b.y; s = s + a.z * b.z; return s; }
+RT_HD V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+// std::max / std::min as the reference calls them (second operand wins only on strict compare)
+RT_HD float maxf_(float a, float b) { return (a < b) ? b : a; }
+RT_HD float minf_(float a, float b) { return (b < a) ? b : a; }
+RT_HD float clampf_(float lo, float hi, float v) { return maxf_(lo, minf_(hi, v)); }   // include/util.h:26-29
+
+// Vec3::length / normalize (include/geometry.h:99-112): double sqrt, double reciprocal
+RT_HD float length(V3 v) { return (float)sqrt((double)dot(v, v)); }
+RT_HD V3 normalize(V3 v)
+{
+    const float l2 = dot(v, v);
+    if (l2 > 0) {
+        const float k = (float)(1.0 / sqrt((double)l2));
+        v.x *= k; v.y *= k; v.z *= k;
+    }
+    return v;
+}
+
+RT_HD float bitsToFloat(uint32_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    union { uint32_t u; float f; } c; c.u = u; return c.f;
+#endif
+}
+// `float < 1e-8` with a DOUBLE literal (objects.cpp:76,79,810): true exactly for floats below the
+// first float above 1e-8, which is 0x322BCC78
+#define RT_EPS_1E8 (rt::bitsToFloat(0x322BCC78u))
+
+// ------------------------------------------------------------------------------------------------
+// device-resident scene description (built by rtb_create from the ABI's RtbScene)
+// ------------------------------------------------------------------------------------------------
+struct Image {
+    unsigned long long tex;      // cudaTextureObject_t: RGBA8, point sampled, unnormalised coords
+    const unsigned char* rgba;   // same texels, linear RGBA8 (host shim / linear fallback for huge maps)
+    int w, h;
+};
+
+struct Object {
+    int type, material;
+    V3 color;
+    float ior, ambient, diffuse, specular, nSpecular;
+    V3 pos;
+    float r2;
+    V3 normal;
+    int mesh;
+};
+
+struct Light {
+    int type;
+    V3 color;
+    float intensity;
+    V3 v;
+    int pointOffset, pointCount;
+};
+
+// Reference-tree node, 32 B: a = (lo.x, lo.y, lo.z, hi.x), b = (hi.y, hi.z, link, count) where link
+// is the right child's index for inner nodes (count < 0) or the first reference slot of a leaf.
+struct Node { float lox, loy, loz, hix, hiy, hiz; int link; int count; };
+
+// One triangle reference slot, 48 B, stored in the reference's leaf order: v0, e1 = v1-v0,
+// e2 = v2-v0 (the same subtractions rayTriangleIntersect performs per test, objects.cpp:70-71).
+struct TriSlot { float v0x, v0y, v0z; int tri; float e1x, e1y, e1z; int pad0; float e2x, e2y, e2z; int pad1; };
+
+struct Mesh {
+    const Node* nodes;
+    const TriSlot* slots;
+    const float* nrm;   // 9 per triangle
+    const float* uv;    // 6 per triangle
+    const float* tan;   // 6 per triangle
+    Image diffuse, normal, specular;
+    int nNodes, nSlots, nTris, maxDepth;
+};
+
+struct Scene {
+    int width, height;
+    float bias;
+    int maxRayDepth;
+    V3 background;
+    unsigned flags;
+    V3 camPos;
+    float camM[16];
+    float camScale, camAspect;
+    int nObjects, nLights, nMeshes;
+    int shadowRaysPerHit;          // sum over lights of (area ? pointCount : 1)
+    const Object* objects;
+    const Light* lights;
+    const Mesh* meshes;
+    const float* areaPoints;
+    Image sky[6];
+};
+
+enum { FLAG_CULL = 1u, FLAG_USE_AC = 2u, FLAG_SKYBOX = 4u, FLAG_SHOW_NORMALS = 8u, FLAG_SSAA = 16u };
+enum { OBJ_SPHERE = 1, OBJ_PLANE = 2, OBJ_MESH = 3 };
+enum { MAT_DIFFUSE = 0, MAT_REFLECTIVE = 1, MAT_TRANSPARENT = 2, MAT_PHONG = 3 };
+enum { LIGHT_DISTANT = 1, LIGHT_POINT = 2, LIGHT_AREA = 3 };
+
+// ------------------------------------------------------------------------------------------------
+// camera: renderWorker's getPixels lambda + Camera::getRay (scene.cpp:453-457, 19-54)
+// ------------------------------------------------------------------------------------------------
+RT_HD V3 mulRowVecMatrix(const float* m, V3 s, bool wZeroColumn)
+{
+    // Matrix44::multVecMatrix (include/geometry.h:289-307)
+    float o[4];
+    for (int j = 0; j < 4; ++j) {
+        float a = s.x * m[0 * 4 + j];
+        a = a + s.y * m[1 * 4 + j];
+        a = a + s.z * m[2 * 4 + j];
+        a = a + m[3 * 4 + j];
+        o[j] = a;
+    }
+    V3 d = mk(o[0], o[1], o[2]);
+    const float w = o[3];
+    (void)wZeroColumn;
+    if (w != 0.0f && w != 1.0f) {
+        const float wi = 1.0f / w;
+        d.x *= wi; d.y *= wi; d.z *= wi;
+    }
+    return d;
+}
+
+// px, py are the values handed to getPixels: (float)x + 0.5f for pass 1, +0.25f / +0.75f for SSAA
+RT_HD V3 cameraDir(const Scene& sc, float px, float py)
+{
+    const float W = (float)sc.width, H = (float)sc.height;
+    const float xPix = (2 * (px + 0.5f) / W - 1) * sc.camScale * sc.camAspect;
+    const float yPix = -(2 * (py + 0.5f) / H - 1) * sc.camScale;
+    return mulRowVecMatrix(sc.camM, normalize(mk(xPix, yPix, -1.0f)), false);
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitives
+// ------------------------------------------------------------------------------------------------
+struct RayCtx {   // ray plus the per-ray invariants intersectBox recomputes per call (objects.cpp:543-544)
+    V3 o, d, inv;
+    int sx, sy, sz;
+};
+RT_HD RayCtx makeRay(V3 o, V3 d)
+{
+    RayCtx r;
+    r.o = o; r.d = d;
+    r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    r.sx = r.inv.x < 0; r.sy = r.inv.y < 0; r.sz = r.inv.z < 0;
+    return r;
+}
+
+// AccelerationStructure::intersectBox (objects.cpp:534-570): ray LINE against the slab box, no t
+// range, comparisons written so NaNs fall through exactly as in the reference.
+RT_HD bool lineHitsBox(const RayCtx& r, float lox, float loy, float loz, float hix, float hiy, float hiz)
+{
+    float tmin = ((r.sx ? hix : lox) - r.o.x) * r.inv.x;
+    float tmax = ((r.sx ? lox : hix) - r.o.x) * r.inv.x;
+    const float tymin = ((r.sy ? hiy : loy) - r.o.y) * r.inv.y;
+    const float tymax = ((r.sy ? loy : hiy) - r.o.y) * r.inv.y;
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
+    const float tzmin = ((r.sz ? hiz : loz) - r.o.z) * r.inv.z;
+    const float tzmax = ((r.sz ? loz : hiz) - r.o.z) * r.inv.z;
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    return true;
+}
+
+// Triangle::rayTriangleIntersect (objects.cpp:59-95), Moller-Trumbore with the reference's reject order
+RT_HD bool hitTriangle(const RayCtx& r, V3 v0, V3 e1, V3 e2, bool cull, float& t, float& u, float& v)
+{
+    const V3 pvec = cross(r.d, e2);
+    const float det = dot(e1, pvec);
+    if (cull && det < RT_EPS_1E8) return false;
+    if (fabsf(det) < RT_EPS_1E8) return false;
+    const float invDet = 1 / det;
+    const V3 tvec = r.o - v0;
+    const float uu = dot(tvec, pvec) * invDet;
+    if (uu < 0 || uu > 1) return false;
+    const V3 qvec = cross(tvec, e1);
+    const float vv = dot(r.d, qvec) * invDet;
+    if (vv < 0 || uu + vv > 1) return false;
+    const float tt = dot(e2, qvec) * invDet;
+    if (tt < 0) return false;
+    t = tt; u = uu; v = vv;
+    return true;
+}
+
+// Sphere::intersectObject (objects.cpp:774-786)
+RT_HD bool hitSphere(const RayCtx& r, V3 c, float r2, float& t)
+{
+    const V3 L = c - r.o;
+    const float tca = dot(L, r.d);
+    const float d2 = dot(L, L) - tca * tca;
+    if (d2 > r2) return false;
+    const float thc = sqrtf(r2 - d2);
+    float t0 = tca - thc;
+    const float t1 = tca + thc;
+    if (t0 < 0) t0 = t1;
+    if (t0 < 0) return false;
+    t = t0;
+    return true;
+}
+
+// Plane::intersectObject (objects.cpp:807-814)
+RT_HD bool hitPlane(const RayCtx& r, V3 p, V3 n, float& t)
+{
+    const float denom = dot(r.d, n);
+    if (fabsf(denom) < RT_EPS_1E8) return false;
+    const float t0 = dot(p - r.o, n) / denom;
+    t = t0;
+    return (t0 >= 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures, skybox
+// ------------------------------------------------------------------------------------------------
+RT_HD void fetchTexel(const Image& im, int x, int y, float& r, float& g, float& b)
+{
+#if defined(__CUDA_ARCH__)
+    if (im.tex) {
+        const uchar4 t = tex2D<uchar4>((cudaTextureObject_t)im.tex, (float)x + 0.5f, (float)y + 0.5f);
+        r = (float)t.x; g = (float)t.y; b = (float)t.z;
+    } else {
+        const uchar4 t = reinterpret_cast<const uchar4*>(im.rgba)[(size_t)y * im.w + x];
+        r = (float)t.x; g = (float)t.y; b = (float)t.z;
+    }
+#else
+    const unsigned char* t = im.rgba + ((size_t)y * im.w + x) * 4;
+    r = (float)t[0]; g = (float)t[1]; b = (float)t[2];
+#endif
+    r /= 256; g /= 256; b /= 256;   // the reference divides by 256, not 255 (objects.cpp:409, scene.cpp:354)
+}
+
+// texel addressing of getDiffuseColor / getSpecularValue / getSurfaceData (objects.cpp:144-147,
+// 156-159): truncation, upper clamp only.  Negative / NaN coordinates index out of bounds in the
+// reference (undefined behaviour); they are clamped to 0 here.
+RT_HD int texIndex(int size, float coord)
+{
+    const float f = size * coord;
+    int i = (f >= 2147483648.0f) ? size : ((f > -2147483648.0f) ? (int)f : 0);
+    if (i >= size) i = size - 1;
+    if (i < 0) i = 0;
+    return i;
+}
+
+// Scene::getSkybox (scene.cpp:381-442)
+RT_HD int skyPixel(float v, int size)
+{
+    const float f = (v + 1.0f) / 2.0f * size;
+    int i = (f >= 2147483648.0f) ? size : ((f > -2147483648.0f) ? (int)f : 0);
+    if (i >= size) i = size - 1;
+    if (i < 0) i = 0;   // reference: out-of-bounds read for directions with a NaN component
+    return i;
+}
+RT_HD V3 skybox(const Scene& sc, V3 dir)
+{
+    if (!(sc.flags & FLAG_SKYBOX)) return sc.background;
+    const float ax = fabsf(dir.x), ay = fabsf(dir.y), az = fabsf(dir.z);
+    const float m = maxf_(ax, maxf_(ay, az));
+    int face, i, j;
+    const int W = sc.sky[0].w, H = sc.sky[0].h;
+    if (m == az) {
+        if (dir.z < 0) { const V3 a = dir * (1 / -dir.z); i = skyPixel(a.y, H); j = skyPixel(a.x, W); face = 1; }
+        else           { const V3 a = dir * (1 / dir.z);  i = skyPixel(a.y, H); j = skyPixel(-a.x, W); face = 3; }
+    } else if (m == ax) {
+        if (dir.x < 0) { const V3 a = dir * (1 / -dir.x); i = skyPixel(a.y, H); j = skyPixel(-a.z, W); face = 0; }
+        else           { const V3 a = dir * (1 / dir.x);  i = skyPixel(a.y, H); j = skyPixel(a.z, W); face = 2; }
+    } else {
+        if (dir.y < 0) { const V3 a = dir * (1 / -dir.y); i = skyPixel(a.z, H); j = skyPixel(a.x, W); face = 5; }
+        else           { const V3 a = dir * (1 / dir.y);  i = skyPixel(a.z, H); j = skyPixel(a.x, W); face = 4; }
+    }
+    V3 c;
+    fetchTexel(sc.sky[face], j, i, c.x, c.y, c.z);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// surface data
+// ------------------------------------------------------------------------------------------------
+struct Surface {
+    V3 P, N, color;
+    float specCoef;
+};
+
+// Object::getSurfaceData + getDiffuseColor + getSpecularValue for all three object kinds
+// (objects.cpp:121-175, 788-796, 816-824; scene.cpp:768-775, 849-851)
+RT_HD Surface surfaceAt(const Scene& sc, const Object& ob, V3 orig, V3 dir, float t, float u, float v, int tri)
+{
+    Surface s;
+    s.P = orig + dir * t;
+    s.color = ob.color;
+    s.specCoef = ob.specular;
+    if (ob.type == OBJ_SPHERE) {
+        s.N = normalize(s.P - ob.pos);
+    } else if (ob.type == OBJ_PLANE) {
+        s.N = ob.normal;
+    } else {
+        const Mesh& me = sc.meshes[ob.mesh];
+        const float* n = me.nrm + (size_t)tri * 9;
+        const float* tc = me.uv + (size_t)tri * 6;
+        const float w = 1 - u - v;
+        V2 tex;
+        tex.x = tc[2] * u + tc[4] * v + tc[0] * w;
+        tex.y = tc[3] * u + tc[5] * v + tc[1] * w;
+        const V3 nb = mk(n[3], n[4], n[5]), nc = mk(n[6], n[7], n[8]), na = mk(n[0], n[1], n[2]);
+        s.N = normalize((nb * u + nc * v + na * w) / 3.0f);
+        if (me.normal.w > 0) {
+            const float* tb = me.tan + (size_t)tri * 6;
+            const int ix = texIndex(me.normal.w, tex.x), iy = texIndex(me.normal.h, tex.y);
+            float r, g, b;
+            fetchTexel(me.normal, ix, iy, r, g, b);
+            // load-time conversion (objects.cpp:431-433) then the lookup's own normalize (:148)
+            V3 tn = normalize(mk(r * 2 - 1, -(g * 2 - 1), b));
+            tn = normalize(tn);
+            // rows tangent, bitangent, N; fourth row and column zero (objects.cpp:133-139)
+            V3 d;
+            d.x = tn.x * tb[0]; d.x = d.x + tn.y * tb[3]; d.x = d.x + tn.z * s.N.x; d.x = d.x + 0.0f;
+            d.y = tn.x * tb[1]; d.y = d.y + tn.y * tb[4]; d.y = d.y + tn.z * s.N.y; d.y = d.y + 0.0f;
+            d.z = tn.x * tb[2]; d.z = d.z + tn.y * tb[5]; d.z = d.z + tn.z * s.N.z; d.z = d.z + 0.0f;
+            float wq = tn.x * 0.0f; wq = wq + tn.y * 0.0f; wq = wq + tn.z * 0.0f; wq = wq + 0.0f;
+            if (wq != 0.0f && wq != 1.0f) { const float wi = 1.0f / wq; d.x *= wi; d.y *= wi; d.z *= wi; }
+            s.N = normalize(d);
+        }
+        if (!(sc.flags & FLAG_SHOW_NORMALS)) {
+            if (me.diffuse.w > 0) {
+                const int ix = texIndex(me.diffuse.w, tex.x), iy = texIndex(me.diffuse.h, tex.y);
+                fetchTexel(me.diffuse, ix, iy, s.color.x, s.color.y, s.color.z);
+            }
+            if (ob.material == MAT_PHONG && me.specular.w > 0) {
+                const int ix = texIndex(me.specular.w, tex.x), iy = texIndex(me.specular.h, tex.y);
+                float r, g, b;
+                fetchTexel(me.specular, ix, iy, r, g, b);
+                s.specCoef = (r + g + b) / 3.0f;   // objects.cpp:455
+            }
+        }
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lights and Fresnel optics
+// ------------------------------------------------------------------------------------------------
+// PointLight::illuminate / DistantLight::illuminate (lights.cpp:18-38).  L is the direction FROM the
+// light; the shadow ray travels along -L up to `dist`.
+RT_HD void illuminate(const Light& li, V3 P, V3& L, V3& I, float& dist)
+{
+    if (li.type == LIGHT_DISTANT) {
+        L = li.v;
+        I = li.color * li.intensity;
+        dist = FLT_MAX;
+    } else {
+        L = P - li.v;
+        const double att = (double)li.intensity / (4 * 3.14159265358979323846 * (double)dot(L, L) / 1000);
+        I = li.color * minf_(1.0f, (float)att);
+        L = normalize(L);
+        dist = length(P - li.v);
+    }
+}
+// intensity of an area light at P (scene.cpp:795, 831, 874, 924)
+RT_HD V3 areaIntensity(const Light& li, V3 P)
+{
+    const V3 d = P - li.v;
+    const double att = (double)li.intensity / (4 * 3.14159265358979323846 * (double)dot(d, d) / 1000);
+    return li.color * minf_(1.0f, (float)att);
+}
+
+RT_HD V3 reflect(V3 dir, V3 n) { return dir - n * (2 * dot(dir, n)); }   // scene.cpp:672-675
+
+RT_HD V3 refract(V3 dir, V3 n, float ior)   // scene.cpp:677-696
+{
+    float n1 = 1, n2 = ior;
+    float cosi = clampf_(-1, 1, dot(dir, n));
+    V3 mn = n;
+    if (cosi < 0) cosi = -cosi;
+    else { const float tmp = n1; n1 = n2; n2 = tmp; mn = -n; }
+    const float rri = n1 / n2;
+    const float k = 1 - rri * rri * (1 - cosi * cosi);
+    if (k < 0) return mk(0.0f, 0.0f, 0.0f);
+    return dir * rri + mn * (rri * cosi - sqrtf(k));
+}
+
+RT_HD float fresnel(V3 dir, V3 n, float ior)   // scene.cpp:698-722
+{
+    float n1 = 1, n2 = ior;
+    float cosi = clampf_(-1, 1, dot(dir, n));
+    if (cosi > 0) { const float tmp = n1; n1 = n2; n2 = tmp; }
+    const float sint = n1 / n2 * sqrtf(maxf_(0.f, 1 - cosi * cosi));
+    if (sint >= 1) return 1;
+    const float cost = sqrtf(maxf_(0.f, 1 - sint * sint));
+    cosi = fabsf(cosi);
+    const float rs = ((n2 * cosi) - (n1 * cost)) / ((n2 * cosi) + (n1 * cost));
+    const float rp = ((n1 * cosi) - (n2 * cost)) / ((n1 * cosi) + (n2 * cost));
+    return (rs * rs + rp * rp) / 2;
+}
+
+// std::pow(float,float) == glibc powf, which is correctly rounded in all but vanishingly rare
+// cases; CUDA's powf is only good to a few ulp, so evaluate in double and round once.
+RT_HD float powExact(float x, float y) { return (float)pow((double)x, (double)y); }
+
+} // namespace rt

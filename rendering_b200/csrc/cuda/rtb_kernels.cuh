@@ -1,0 +1,523 @@
+// rtb_kernels.cuh — wavefront ray-tracing kernels (sm_100a).
+//
+// The reference renders one pixel at a time with a recursive castRay (scene.cpp:758-946).  Here a
+// frame is a sequence of breadth-first LEVELS (level = recursion depth); each level runs as
+// separate kernels over compacted queues:
+//
+//   k_raygen / k_ssaa_gen   primary rays                      (renderWorker, SSAAworker)
+//   k_trace                 closest hit over all objects      (Render::trace + intersectAccelStruct)
+//   k_surface               hit -> surface record, miss -> skybox; compacts hits   (castRay :762-775, :945)
+//   k_shadow                any-hit shadow rays, one per (surface, light sample)   (castRay :785-787 ...)
+//   k_shade                 light accumulation per material; resolves Diffuse/Phong, spawns the
+//                           Reflective / Transparent children into the next level's queue
+//   k_combine               folds child colours into their parents, deepest level first, with the
+//                           reference's exact expression order (:858-890, :896-940)
+//   k_sobel                 edge mask + compaction of flagged pixels   (launchSSAA :554-568)
+//   k_ssaa_resolve          mean of the 4 re-traced samples            (SSAAworker :525-536)
+//
+// Colours travel through a "slot" array (3 floats per slot): slots [0, w*h) are the framebuffer,
+// the rest is bump-allocated for SSAA samples and for the children of Reflective / Transparent hits.
+// Every ray carries the slot its colour must land in, so queue order never affects the image.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "rt_device.cuh"
+
+namespace rtk {
+
+using namespace rt;
+
+constexpr int kBlock = 128;          // threads per CTA for the ray kernels
+constexpr int kStackDepth = 64;      // per-thread traversal stack entries (shared memory)
+
+// Device-side bump counters.  Reset / read back by the host once per level.
+struct Counters {
+    int nextRays;        // rays appended to the next level's queue
+    int surfaces;        // compacted hits of this level
+    int interiors;       // Reflective / Transparent records (persist until k_combine)
+    int slots;           // colour slots handed out
+    int ssaaPixels;      // pixels flagged by k_sobel
+    int overflow;        // set when a queue would overflow its capacity
+    unsigned long long boxTests, triTests;
+};
+
+// Structure-of-arrays ray queue (one level).
+struct RayQueue {
+    float4* o;       // origin.xyz
+    float4* d;       // direction.xyz
+    int* dest;       // colour slot
+};
+
+struct HitQueue {
+    float4* tuv;     // t, u, v, triangle index (int bits)
+    int* obj;        // object index, -1 = miss
+};
+
+struct SurfQueue {
+    float4* pS;      // P.xyz, specular coefficient
+    float4* nO;      // N.xyz, object index (int bits)
+    float4* cR;      // colour.xyz, ray index (int bits)
+};
+
+// Reflective / Transparent hit waiting for its children (castRay's stack frame).
+struct Interior {
+    int dest;        // slot of this ray's own colour
+    int child;       // first child slot: [child] refraction (or the single reflection), [child+1] reflection
+    int kind;        // 1 = Reflective, 2 = Transparent with refraction, 3 = Transparent, total internal reflection
+    float kr;
+    float sx, sy, sz;   // specular light sum
+};
+
+__device__ __forceinline__ void storeSlot(float* slots, int s, V3 c)
+{
+    float* p = slots + (size_t)s * 3;
+    p[0] = c.x; p[1] = c.y; p[2] = c.z;
+}
+__device__ __forceinline__ V3 loadSlot(const float* slots, int s)
+{
+    const float* p = slots + (size_t)s * 3;
+    return mk(p[0], p[1], p[2]);
+}
+
+// warp-aggregated bump allocation: one atomicAdd per warp for `n` items per participating lane
+__device__ __forceinline__ int warpAlloc(int* counter, bool want, int n)
+{
+    const unsigned mask = __activemask();
+    const unsigned votes = __ballot_sync(mask, want);
+    if (votes == 0) return -1;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(votes) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(votes) * n);
+    base = __shfl_sync(mask, base, leader);
+    return want ? base + __popc(votes & ((1u << lane) - 1)) * n : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray generation
+// ------------------------------------------------------------------------------------------------
+// rows[] lists the image rows to render (each < height-1); every row has width-1 pixels because the
+// reference never renders the last column / row (getTiles, scene.cpp:369-372).
+__global__ void k_raygen(Scene sc, const int* __restrict__ rows, int nRows, RayQueue q)
+{
+    const int wm1 = sc.width - 1;
+    const long long total = (long long)nRows * wm1;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / wm1), x = (int)(i % wm1);
+        const int y = rows[r];
+        const V3 d = cameraDir(sc, (float)x + 0.5f, (float)y + 0.5f);
+        q.o[i] = make_float4(sc.camPos.x, sc.camPos.y, sc.camPos.z, 0.0f);
+        q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+        q.dest[i] = y * sc.width + x;
+    }
+}
+
+// caller-supplied rays (rtb_trace / rtb_cast): 6 floats per ray
+__global__ void k_rays_from_user(const float* __restrict__ rays, int n, int destBase, RayQueue q)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        q.o[i] = make_float4(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2], 0.0f);
+        q.d[i] = make_float4(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5], 0.0f);
+        q.dest[i] = destBase + i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// traversal
+// ------------------------------------------------------------------------------------------------
+// Walks one mesh's reference tree exactly like intersectAccelStruct (objects.cpp:587-631): every
+// node whose box the ray LINE overlaps is visited, left before right, every triangle of every such
+// leaf is tested, the first strictly smaller t wins.  ANY: stop at the first t < tLimit (shadow).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ bool walkMesh(const Scene& sc, const Mesh& me, const RayCtx& r, int* stack, float tLimit,
+    float& tBest, float& uBest, float& vBest, int& triBest, unsigned long long& nBox, unsigned long long& nTri)
+{
+    if (me.nNodes == 0) return false;
+    const bool useAC = sc.flags & FLAG_USE_AC;
+    const bool cull = sc.flags & FLAG_CULL;
+    bool found = false;
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(me.nodes) + 2 * node);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(me.nodes) + 2 * node + 1);
+        if (COUNT && useAC) nBox++;
+        const bool inside = !useAC || lineHitsBox(r, a.x, a.y, a.z, a.w, b.x, b.y);
+        if (inside) {
+            const int link = __float_as_int(b.z), count = __float_as_int(b.w);
+            if (count < 0) {
+                stack[sp * kBlock] = link;
+                sp++;
+                node = node + 1;
+                continue;
+            }
+            const float4* slot = reinterpret_cast<const float4*>(me.slots) + (size_t)link * 3;
+            for (int s = 0; s < count; ++s, slot += 3) {
+                const float4 p0 = __ldg(slot), p1 = __ldg(slot + 1), p2 = __ldg(slot + 2);
+                float t, u, v;
+                if (COUNT) nTri++;
+                if (hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) {
+                    if (ANY) {
+                        if (t < tLimit) { if (!COUNT) return true; found = true; }
+                    } else if (t < tBest) {
+                        tBest = t; uBest = u; vBest = v; triBest = __float_as_int(p0.w); found = true;
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        sp--;
+        node = stack[sp * kBlock];
+    }
+    return found;
+}
+
+// Render::trace for primary / secondary rays (scene.cpp:724-756)
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int n, HitQueue hits, Counters* ctr)
+{
+    __shared__ int stackMem[kStackDepth * kBlock];
+    int* stack = stackMem + threadIdx.x;
+    unsigned long long nBox = 0, nTri = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 o4 = q.o[i], d4 = q.d[i];
+        const RayCtx r = makeRay(mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z));
+        float tNear = FLT_MAX, uN = -1.0f, vN = -1.0f;
+        int objN = -1, triN = -1;
+        for (int k = 0; k < sc.nObjects; ++k) {
+            const Object& ob = sc.objects[k];
+            float t = FLT_MAX, u = 0.0f, v = 0.0f;
+            int tri = -1;
+            bool ok;
+            if (ob.type == OBJ_MESH) ok = walkMesh<false, COUNT>(sc, sc.meshes[ob.mesh], r, stack, 0.0f, t, u, v, tri, nBox, nTri);
+            else if (ob.type == OBJ_SPHERE) ok = hitSphere(r, ob.pos, ob.r2, t);
+            else ok = hitPlane(r, ob.pos, ob.normal, t);
+            if (ok && t < tNear) { tNear = t; uN = u; vN = v; objN = k; triN = tri; }
+        }
+        hits.tuv[i] = make_float4(tNear, uN, vN, __int_as_float(triN));
+        hits.obj[i] = objN;
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->boxTests, nBox);
+        atomicAdd(&ctr->triTests, nTri);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// surface stage: castRay between trace() and the light loops (scene.cpp:762-775, 945)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int n, HitQueue hits, SurfQueue surf,
+    float* __restrict__ slots, Counters* ctr)
+{
+    const int nPadded = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPadded; i += gridDim.x * blockDim.x) {
+        bool wantSurface = false;
+        Surface s;
+        int obj = -1;
+        if (i < n) {
+            obj = hits.obj[i];
+            const float4 d4 = q.d[i];
+            const V3 d = mk(d4.x, d4.y, d4.z);
+            if (obj < 0) {
+                storeSlot(slots, q.dest[i], skybox(sc, d));
+            } else {
+                const float4 o4 = q.o[i], h = hits.tuv[i];
+                s = surfaceAt(sc, sc.objects[obj], mk(o4.x, o4.y, o4.z), d, h.x, h.y, h.z, __float_as_int(h.w));
+                if (sc.flags & FLAG_SHOW_NORMALS) storeSlot(slots, q.dest[i], s.N / 2.0f + mk(0.5f, 0.5f, 0.5f));
+                else wantSurface = true;
+            }
+        }
+        const int si = warpAlloc(&ctr->surfaces, wantSurface, 1);
+        if (wantSurface) {
+            surf.pS[si] = make_float4(s.P.x, s.P.y, s.P.z, s.specCoef);
+            surf.nO[si] = make_float4(s.N.x, s.N.y, s.N.z, __int_as_float(obj));
+            surf.cR[si] = make_float4(s.color.x, s.color.y, s.color.z, __int_as_float(i));
+        }
+    }
+}
+
+// light sample k of a surface: direction FROM the light (normalised for point / area) and distance
+__device__ __forceinline__ void shadowSample(const Scene& sc, int k, V3 P, V3& L, float& dist)
+{
+    for (int i = 0; i < sc.nLights; ++i) {
+        const Light& li = sc.lights[i];
+        const int cnt = (li.type == LIGHT_AREA) ? li.pointCount : 1;
+        if (k < cnt) {
+            if (li.type == LIGHT_AREA) {
+                const float* ap = sc.areaPoints + (size_t)(li.pointOffset + k) * 3;
+                L = P - mk(ap[0], ap[1], ap[2]);
+                dist = length(L);            // intrShadInfo.tNear = lightDir.length()   (scene.cpp:800)
+                L = normalize(L);
+            } else {
+                V3 I;
+                illuminate(li, P, L, I, dist);
+            }
+            return;
+        }
+        k -= cnt;
+    }
+}
+
+// Shadow trace (scene.cpp:787 etc.): Transparent objects cast no shadow (:733); an occluder counts
+// only when it is closer than the light (`tNear < intrInfo.tNear`, tNear preloaded by illuminate).
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, SurfQueue surf, unsigned char* __restrict__ vis, Counters* ctr)
+{
+    __shared__ int stackMem[kStackDepth * kBlock];
+    int* stack = stackMem + threadIdx.x;
+    unsigned long long nBox = 0, nTri = 0;
+    const int S = sc.shadowRaysPerHit;
+    const long long total = (long long)ctr->surfaces * S;
+    for (long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x; qi < total; qi += (long long)gridDim.x * blockDim.x) {
+        const int si = (int)(qi / S), k = (int)(qi % S);
+        const float4 p4 = surf.pS[si], n4 = surf.nO[si];
+        const V3 P = mk(p4.x, p4.y, p4.z), N = mk(n4.x, n4.y, n4.z);
+        V3 L; float dist;
+        shadowSample(sc, k, P, L, dist);
+        const RayCtx r = makeRay(P + N * sc.bias, -L);
+        float tNear = dist;
+        bool blocked = false;
+        for (int j = 0; j < sc.nObjects; ++j) {
+            const Object& ob = sc.objects[j];
+            if (ob.material == MAT_TRANSPARENT) continue;
+            float t = FLT_MAX, u, v; int tri;
+            bool ok;
+            if (ob.type == OBJ_MESH) {
+                if (COUNT) {
+                    // full closest-hit walk so the work counters equal the reference's
+                    ok = walkMesh<false, true>(sc, sc.meshes[ob.mesh], r, stack, 0.0f, t, u, v, tri, nBox, nTri);
+                } else {
+                    ok = walkMesh<true, false>(sc, sc.meshes[ob.mesh], r, stack, tNear, t, u, v, tri, nBox, nTri);
+                    if (ok) { blocked = true; break; }
+                    continue;
+                }
+            } else if (ob.type == OBJ_SPHERE) ok = hitSphere(r, ob.pos, ob.r2, t);
+            else ok = hitPlane(r, ob.pos, ob.normal, t);
+            if (ok && t < tNear) { tNear = t; blocked = true; if (!COUNT) break; }
+        }
+        vis[qi] = blocked ? 0 : 1;
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->boxTests, nBox);
+        atomicAdd(&ctr->triTests, nTri);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade stage: the four material branches of castRay (scene.cpp:780-941)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_shade(Scene sc, RayQueue q, SurfQueue surf, const unsigned char* __restrict__ vis,
+    int depth, RayQueue next, int nextCap, Interior* __restrict__ interiors, int interiorCap,
+    float* __restrict__ slots, int slotCap, Counters* ctr)
+{
+    const int S = sc.shadowRaysPerHit;
+    const int n = ctr->surfaces;
+    const int nPadded = (n + 31) & ~31;
+    for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < nPadded; si += gridDim.x * blockDim.x) {
+        int nChildren = 0;
+        bool wantInterior = false;
+        Interior rec;
+        V3 childO[2], childD[2];
+        if (si < n) {
+            const float4 p4 = surf.pS[si], n4 = surf.nO[si], c4 = surf.cR[si];
+            const V3 P = mk(p4.x, p4.y, p4.z), N = mk(n4.x, n4.y, n4.z), color = mk(c4.x, c4.y, c4.z);
+            const Object& ob = sc.objects[__float_as_int(n4.w)];
+            const int ri = __float_as_int(c4.w);
+            const float4 d4 = q.d[ri];
+            const V3 dir = mk(d4.x, d4.y, d4.z);
+            const int dest = q.dest[ri];
+            const int mat = ob.material;
+
+            V3 diff = mk(0.0f, 0.0f, 0.0f), spec = mk(0.0f, 0.0f, 0.0f);
+            int k = 0;
+            for (int i = 0; i < sc.nLights; ++i) {
+                const Light& li = sc.lights[i];
+                if (li.type != LIGHT_AREA) {
+                    V3 L, I; float dist;
+                    illuminate(li, P, L, I, dist);
+                    const float v = vis[(size_t)si * S + k] ? 1.0f : 0.0f;
+                    k++;
+                    if (mat == MAT_DIFFUSE) {
+                        diff = diff + I * (v * maxf_(0.f, dot(N, -L)));                       // :788
+                    } else {
+                        if (mat == MAT_PHONG) diff = diff + (I * v) * maxf_(0.f, dot(N, -L)); // :820
+                        const V3 R = reflect(L, N);
+                        spec = spec + (I * v) * powExact(maxf_(0.f, dot(R, -dir)), ob.nSpecular);   // :824, :867, :917
+                    }
+                } else {
+                    const V3 I = areaIntensity(li, P);
+                    float dsum = 0.0f, ssum = 0.0f;
+                    for (int p = 0; p < li.pointCount; ++p, ++k) {
+                        const float* ap = sc.areaPoints + (size_t)(li.pointOffset + p) * 3;
+                        const V3 L = normalize(P - mk(ap[0], ap[1], ap[2]));
+                        const float v = vis[(size_t)si * S + k] ? 1.0f : 0.0f;
+                        dsum += v * maxf_(0.f, dot(N, -L));
+                        const V3 R = reflect(L, N);
+                        ssum += v * maxf_(0.f, dot(R, -dir));
+                    }
+                    const float cnt = (float)li.pointCount;
+                    if (mat == MAT_DIFFUSE || mat == MAT_PHONG) diff = diff + I * (dsum / cnt);      // :806, :844
+                    if (mat != MAT_DIFFUSE) spec = spec + I * powExact(ssum / cnt, ob.nSpecular);     // :846, :887, :937
+                }
+            }
+
+            if (mat == MAT_DIFFUSE) {
+                storeSlot(slots, dest, color * diff);                                                 // :809
+            } else if (mat == MAT_PHONG) {
+                storeSlot(slots, dest, color * ob.ambient + diff * ob.diffuse + spec * p4.w);         // :852
+            } else if (mat == MAT_REFLECTIVE) {
+                const V3 ro = P + N * sc.bias;
+                const V3 rd = dir - N * (2 * dot(dir, N));                                           // :856
+                if (depth + 1 > sc.maxRayDepth) {
+                    storeSlot(slots, dest, skybox(sc, rd) * 0.8f + spec);                             // :760, :858, :890
+                } else {
+                    wantInterior = true; nChildren = 1;
+                    rec.dest = dest; rec.kind = 1; rec.kr = 0.0f; rec.sx = spec.x; rec.sy = spec.y; rec.sz = spec.z;
+                    childO[0] = ro; childD[0] = rd;
+                }
+            } else {
+                const float kr = fresnel(dir, N, ob.ior);                                             // :893
+                const bool outside = dot(dir, N) < 0;
+                const V3 biasVec = N * sc.bias;
+                const bool refr = kr < 1;
+                V3 rdir = mk(0.0f, 0.0f, 0.0f), rorig = P;
+                if (refr) {
+                    rdir = normalize(refract(dir, N, ob.ior));                                        // :899
+                    rorig = outside ? P - biasVec : P + biasVec;
+                }
+                const V3 fdir = normalize(reflect(dir, N));                                           // :905
+                const V3 forig = outside ? P + biasVec : P - biasVec;
+                if (depth + 1 > sc.maxRayDepth) {
+                    V3 c = mk(0.0f, 0.0f, 0.0f);
+                    if (refr) c = c + skybox(sc, rdir) * (1 - kr);
+                    c = c + skybox(sc, fdir) * kr;
+                    c = c + spec * kr;
+                    storeSlot(slots, dest, c);
+                } else {
+                    wantInterior = true;
+                    rec.dest = dest; rec.kr = kr; rec.sx = spec.x; rec.sy = spec.y; rec.sz = spec.z;
+                    if (refr) { rec.kind = 2; nChildren = 2; childO[0] = rorig; childD[0] = rdir; childO[1] = forig; childD[1] = fdir; }
+                    else { rec.kind = 3; nChildren = 1; childO[0] = forig; childD[0] = fdir; }
+                }
+            }
+        }
+        // bump-allocate: interior record, two colour slots, nChildren queue entries
+        const int ii = warpAlloc(&ctr->interiors, wantInterior, 1);
+        const int cs = warpAlloc(&ctr->slots, wantInterior, 2);
+        const int q1 = warpAlloc(&ctr->nextRays, nChildren >= 1, 1);
+        const int q2 = warpAlloc(&ctr->nextRays, nChildren >= 2, 1);
+        if (wantInterior) {
+            if (ii >= interiorCap || cs + 2 > slotCap || (nChildren >= 1 && q1 >= nextCap) || (nChildren >= 2 && q2 >= nextCap)) {
+                ctr->overflow = 1;
+            } else {
+                rec.child = cs;
+                interiors[ii] = rec;
+                // kind 3 keeps its single (reflection) child in slot child+1 so k_combine reads one layout
+                const int firstSlot = (rec.kind == 3) ? cs + 1 : cs;
+                next.o[q1] = make_float4(childO[0].x, childO[0].y, childO[0].z, 0.0f);
+                next.d[q1] = make_float4(childD[0].x, childD[0].y, childD[0].z, 0.0f);
+                next.dest[q1] = firstSlot;
+                if (nChildren == 2) {
+                    next.o[q2] = make_float4(childO[1].x, childO[1].y, childO[1].z, 0.0f);
+                    next.d[q2] = make_float4(childD[1].x, childD[1].y, childD[1].z, 0.0f);
+                    next.dest[q2] = cs + 1;
+                }
+            }
+        }
+    }
+}
+
+// Fold children into parents for interior records [first, last): castRay's return path.
+__global__ void k_combine(const Interior* __restrict__ interiors, int first, int last, float* __restrict__ slots)
+{
+    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < last; i += gridDim.x * blockDim.x) {
+        const Interior rec = interiors[i];
+        const V3 spec = mk(rec.sx, rec.sy, rec.sz);
+        V3 c;
+        if (rec.kind == 1) {
+            c = loadSlot(slots, rec.child) * 0.8f;                 // hitColor = 0.8f * castRay(...)   (:858)
+            c = c + spec;                                          // hitColor += specularComponent    (:890)
+        } else {
+            c = mk(0.0f, 0.0f, 0.0f);                              // hitColor = { 0 }                 (:896)
+            if (rec.kind == 2) c = c + loadSlot(slots, rec.child) * (1 - rec.kr);   // :902
+            c = c + loadSlot(slots, rec.child + 1) * rec.kr;       // :908
+            c = c + spec * rec.kr;                                 // :940
+        }
+        storeSlot(slots, rec.dest, c);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SSAA: Sobel mask on the unclamped float frame, then 4 re-traced samples per flagged pixel
+// ------------------------------------------------------------------------------------------------
+// rows[]: image rows owned by this call; only interior pixels get a flag (scene.cpp:554-555)
+__global__ void k_sobel(int width, int height, const float* __restrict__ fb, const int* __restrict__ rows, int nRows,
+    int* __restrict__ flagged, Counters* ctr)
+{
+    const long long total = (long long)nRows * width;
+    const long long padded = (total + 31) & ~31LL;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < padded; i += (long long)gridDim.x * blockDim.x) {
+        bool flag = false;
+        int pix = 0;
+        if (i < total) {
+            const int y = rows[i / width], x = (int)(i % width);
+            if (y >= 1 && y < height - 1 && x >= 1 && x < width - 1) {
+                V3 gx = mk(0.0f, 0.0f, 0.0f), gy = mk(0.0f, 0.0f, 0.0f);
+                const float op[3][3] = { { -1, 0, 1 }, { -2, 0, 2 }, { -1, 0, 1 } };
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const V3 c = loadSlot(fb, (y - 1 + a) * width + x - 1 + b);
+                        gx = gx + c * op[a][b];
+                        gy = gy + c * op[b][a];
+                    }
+                const float lx = length(gx), ly = length(gy);
+                // powf(v, 2) of the reference is v*v to within glibc's rounding (scene.cpp:565)
+                flag = sqrtf(lx * lx + ly * ly) > 0.5f;
+                pix = y * width + x;
+            }
+        }
+        const int f = warpAlloc(&ctr->ssaaPixels, flag, 1);
+        if (flag) flagged[f] = pix;
+    }
+}
+
+__global__ void k_ssaa_gen(Scene sc, const int* __restrict__ flagged, int nFlagged, int slotBase, RayQueue q)
+{
+    const int total = nFlagged * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int pix = flagged[i >> 2], k = i & 3;
+        const int y = pix / sc.width, x = pix % sc.width;
+        // sample order (.25,.25) (.25,.75) (.75,.25) (.75,.75)  (scene.cpp:527-534)
+        const float ox = (k & 2) ? 0.75f : 0.25f, oy = (k & 1) ? 0.75f : 0.25f;
+        const V3 d = cameraDir(sc, (float)x + ox, (float)y + oy);
+        q.o[i] = make_float4(sc.camPos.x, sc.camPos.y, sc.camPos.z, 0.0f);
+        q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+        q.dest[i] = slotBase + i;
+    }
+}
+
+__global__ void k_ssaa_resolve(const int* __restrict__ flagged, int nFlagged, int slotBase, float* __restrict__ slots)
+{
+    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nFlagged; f += gridDim.x * blockDim.x) {
+        V3 c = mk(0.0f, 0.0f, 0.0f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c = c + loadSlot(slots, slotBase + f * 4 + k);
+        storeSlot(slots, flagged[f], c / 4.0f);
+    }
+}
+
+// copy owned rows of the full-frame slot region into a compact output
+__global__ void k_gather_rows(const float* __restrict__ fb, int width, const int* __restrict__ rows, int nRows, float* __restrict__ out)
+{
+    const long long rowFloats = (long long)width * 3;
+    const long long total = (long long)nRows * rowFloats;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / rowFloats);
+        out[i] = fb[(long long)rows[r] * rowFloats + (i % rowFloats)];
+    }
+}
+
+} // namespace rtk
