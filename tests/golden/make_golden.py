@@ -1,0 +1,83 @@
+"""Generates tests/golden/*.npz + golden.json by running the UNMODIFIED reference
+(oracle/_ref/ref_driver, built from /root/reference by oracle/Makefile) on the config scenes.
+Only runs where /root/reference exists (the build container); the fixtures are committed.
+
+    python tests/golden/make_golden.py
+
+Small cases store the reference's float framebuffers (pass 1 and final); full-size configs store
+sha256 digests, float sums and the reference's own work counters (collectStatistics).
+"""
+import hashlib
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SCENES = os.path.join(ROOT, "scenes")
+DRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+# name -> (config scene, width, height, store framebuffers?)
+CASES = {
+    "cfg1_256": ("cfg1_simple_shapes_256", 256, 256, True),
+    "cfg2_128": ("cfg2_smooth_shading_1024", 128, 128, True),
+    "cfg3_240": ("cfg3_reflective_refractive_1080", 240, 136, True),
+    "cfg4_240": ("cfg4_shotgun_1080", 240, 136, True),
+    "cfgD_160": ("cfgD_dragon_1080", 160, 92, True),
+    "cfg2_1024": ("cfg2_smooth_shading_1024", 1024, 1024, False),
+    "cfg3_1080": ("cfg3_reflective_refractive_1080", 1920, 1080, False),
+    "cfg4_1080": ("cfg4_shotgun_1080", 1920, 1080, False),
+}
+
+
+def resized_scene(cfg, w, h, tmpdir, name):
+    text = open(os.path.join(SCENES, cfg + ".scene")).read()
+    text = re.sub(r"(?m)^width=.*$", f"width={w}", text)
+    text = re.sub(r"(?m)^height=.*$", f"height={h}", text)
+    path = os.path.join(SCENES, f"_golden_{name}.scene")   # must sit in scenes/ (asset paths are cwd-relative)
+    open(path, "w").write(text)
+    return path
+
+
+# The reference's Sobel mask is `new bool[w*h]` with an uninitialised border (scene.cpp:545,554): small
+# frames reuse dirty heap chunks and flag random row-0 / column-0 pixels.  MALLOC_PERTURB_=255 makes
+# glibc fill every allocation with 0xff ^ 0xff = 0, i.e. the canonical "border flags are false" run.
+ENV = dict(os.environ, MALLOC_PERTURB_="255")
+
+
+def main():
+    out = {}
+    tmp = tempfile.mkdtemp()
+    for name, (cfg, w, h, store) in CASES.items():
+        path = resized_scene(cfg, w, h, tmp, name)
+        try:
+            prefix = os.path.join(tmp, name)
+            info = json.loads(subprocess.run([DRV, "render", os.path.basename(path), prefix, "1"], cwd=SCENES, check=True, env=ENV,
+                                             capture_output=True, text=True).stdout.strip().splitlines()[-1])
+            stats = json.loads(subprocess.run([DRV, "stats", os.path.basename(path), "1"], cwd=SCENES, check=True, env=ENV,
+                                              capture_output=True, text=True).stdout.strip().splitlines()[-1])
+            p1 = np.fromfile(prefix + ".pass1.f32", np.float32).reshape(h, w, 3)
+            fin = np.fromfile(prefix + ".final.f32", np.float32).reshape(h, w, 3)
+            out[name] = {
+                "scene": cfg, "width": w, "height": h,
+                "pass1_sha256": hashlib.sha256(p1.tobytes()).hexdigest(),
+                "final_sha256": hashlib.sha256(fin.tobytes()).hexdigest(),
+                "pass1_sum": float(p1.astype(np.float64).sum()), "final_sum": float(fin.astype(np.float64).sum()),
+                "rays": stats["rays"], "box_tests": stats["box_tests"], "tri_tests": stats["tri_tests"],
+                "ssaa_pixels": int((p1.view(np.uint32) != fin.view(np.uint32)).any(axis=2).sum()),
+            }
+            if store:
+                np.savez_compressed(os.path.join(HERE, name + ".npz"), pass1=p1, final=fin)
+            print(name, out[name], flush=True)
+        finally:
+            os.remove(path)
+    json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -22,7 +22,7 @@ def ref_render(cfg, tmp):
     drv = os.path.join(rb.REPO_ROOT, "oracle", "_ref", "ref_driver")
     prefix = os.path.join(tmp, cfg)
     t = time.time()
-    out = subprocess.run([drv, "render", cfg + ".scene", prefix, "1" if "cfg3" in cfg else "0"], cwd=rb.SCENES_DIR,
+    out = subprocess.run([drv, "render", cfg + ".scene", prefix, "1" if "cfg3" in cfg else "0"], cwd=rb.SCENES_DIR, env=dict(os.environ, MALLOC_PERTURB_='255'),
                          check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1]
     info = json.loads(out)
     info["wall_s"] = time.time() - t
