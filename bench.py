@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s and ms/frame of the Scene::render hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--scene cfg4_shotgun_1080] [--impl reference]
+
+One "step" = one frame: pass 1 (launchWorkers) + Sobel + SSAA re-trace (launchSSAA) of the workload
+scene at 1920x1080.  Rays = the number of Render::trace invocations the REFERENCE makes for that
+frame (primary + secondary + shadow + SSAA) — the CUDA path reproduces that count
+exactly (tests/test_gpu_parity.py), so both arms share the numerator.
+
+ours:       value  = rays / device time, scene and queues resident in HBM, framebuffer left in HBM,
+                     CUDA events on the render stream, L2 flushed between timed frames.
+            e2e    = the same frame through the public host-buffer call (rtb_render with a pinned
+                     HOST framebuffer: row lists / counters H2D, framebuffer D2H inside the call).
+            roofline = the traversal kernel (k_trace, Render::trace for primary/secondary rays),
+                     algorithmic bytes from the reference's own work counts:
+                     48 B/ray + 32 B/box test + 48 B/triangle test, over its CUDA-event time.
+reference:  oracle/_ref/ref_driver (the unmodified reference sources, compiled by oracle/Makefile)
+            timing launchWorkers + launchSSAA on all host cores; the oracle port when that binary
+            is absent.
+N > 1:      rows are dealt to ranks in cyclic strips, each rank renders its strips, one
+            torch.distributed gather (NCCL) assembles the frame on rank 0; strong scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s"
+DEFAULT_SCENE = "cfg4_shotgun_1080"
+GOLDEN_KEY = {"cfg4_shotgun_1080": "cfg4_1080", "cfg2_smooth_shading_1024": "cfg2_1024",
+              "cfg3_reflective_refractive_1080": "cfg3_1080", "cfg1_simple_shapes_256": "cfg1_256"}
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default=DEFAULT_SCENE)
+    ap.add_argument("--strip-rows", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def golden_rays(scene):
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))
+        return int(g[GOLDEN_KEY[scene]]["rays"])
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+# ------------------------------------------------------------------------------------------------
+def run_reference(scene, frames, warmup, rays):
+    """Times the reference's own CPU implementation.  Returns (ms per frame list, info dict)."""
+    cores = os.cpu_count() or 1
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    scenes_dir = os.path.join(ROOT, "scenes")
+    if os.path.exists(drv):
+        out = subprocess.run([drv, "bench", scene + ".scene", str(frames + warmup), str(cores)], cwd=scenes_dir, check=True,
+                             capture_output=True, text=True).stdout.strip().splitlines()[-1]
+        info = json.loads(out)
+        ms = info["frame_ms"][warmup:]
+        if rays is None:
+            st = json.loads(subprocess.run([drv, "stats", scene + ".scene", str(cores)], cwd=scenes_dir, check=True,
+                                           capture_output=True, text=True).stdout.strip().splitlines()[-1])
+            rays = st["rays"]
+        return ms, {"kind": "reference", "cores": info["workers"], "rays": rays,
+                    "sample": f"{len(ms)} full frames of {scene} (launchWorkers + launchSSAA), std::thread tile renderer, "
+                              f"{info['workers']} workers, after {warmup} warm-up frame(s)"}
+    # fall back to the oracle port (plain-C restatement, pthreads over rows)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rendering_b200 as rb
+    from helpers import oracle_render
+    sc = rb.Scene(rb.scene_path(scene))
+    ms = []
+    for i in range(frames + warmup):
+        t = time.perf_counter()
+        _, _, cnt = oracle_render(sc, threads=cores)
+        if i >= warmup:
+            ms.append((time.perf_counter() - t) * 1e3)
+    return ms, {"kind": "port", "cores": cores, "rays": cnt["rays"],
+                "sample": f"{len(ms)} full frames of {scene}, oracle/rtb_oracle.c with {cores} pthreads"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rays = golden_rays(args.scene)
+    ms, info = run_reference(args.scene, args.steps, max(1, args.warmup), rays)
+    rays = info.pop("rays")
+    mean_ms = sum(ms) / len(ms)
+    value = rays / (mean_ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "reference assets (scenes/input), no randomness",
+        "config": {"workload": f"{args.scene}: 1920x1080 frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays},
+        "cpu_baseline": dict(info, value=value, unit="Mrays/s"),
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.thread = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import rendering_b200 as rb
+    from rendering_b200 import dist as rdist
+    from rendering_b200._ffi import KERNEL_KINDS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the renderer has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    sc = rb.Scene(rb.scene_path(args.scene))
+    h, w = sc.height, sc.width
+    stream = torch.cuda.Stream()
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    # reference-defined work of the frame, per kernel kind (outside the timed region)
+    counted = rb.Renderer(sc, device=local, counters=True)
+    _, cst = counted.render()
+    counted.close()
+    rays = cst["rays"]
+    closest_rays = cst["primaryRays"] + cst["secondaryRays"]
+    trace_bytes = 48 * closest_rays + 32 * (cst["boxTests"] - cst["boxTestsShadow"]) + 48 * (cst["triTests"] - cst["triTestsShadow"])
+    shadow_bytes = 48 * cst["shadowRays"] + 32 * cst["boxTestsShadow"] + 48 * cst["triTestsShadow"]
+
+    r = rb.Renderer(sc, device=local)
+    nrows_max = rdist.max_rows(h, args.strip_rows, world)
+    out = torch.empty((nrows_max if world > 1 else h, w, 3), dtype=torch.float32, device="cuda")
+
+    def step():
+        if world == 1:
+            return r.render_device(out.data_ptr(), stream=stream.cuda_stream), None
+        st = r.render_strips_device(out.data_ptr(), args.strip_rows, rank, world, stream=stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            frame = rdist.gather_frame(out, h, args.strip_rows, rank, world)
+        return st, frame
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    kernel_ms = [0.0] * len(KERNEL_KINDS)
+    kernel_launches = [0] * len(KERNEL_KINDS)
+    launches = 0
+    total_ms = 0.0
+    sampler = ClockSampler(local)
+    with sampler:
+        barrier()
+        for _ in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()                      # evict L2 (256 MiB written, L2 is 126 MB); not timed
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            st, _ = step()
+            e1.record(stream)
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+            launches += st["kernelLaunches"]
+            for k in range(len(KERNEL_KINDS)):
+                kernel_ms[k] += st["msKernel"][k]
+                kernel_launches[k] += st["launchesKernel"][k]
+        barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = rays / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the public host-buffer call ----------------------------------------
+    host_fb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+    host_np = host_fb.numpy()
+    e2e_ms = 0.0
+    h2d = d2h = 0
+    for i in range(args.steps + 1):
+        barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            _, est = r.render(out=host_np)
+            h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
+        else:
+            est, frame = step()
+            h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
+            if rank == 0:
+                host_fb.copy_(frame, non_blocking=False)
+                d2h_i += host_fb.numel() * 4
+        barrier()
+        if i > 0:
+            e2e_ms += (time.perf_counter() - t0) * 1e3
+            h2d, d2h = h2d_i, d2h_i
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(te.item()) / args.steps
+    e2e_value = rays / (e2e_ms_per_step * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    k_trace = KERNEL_KINDS.index("trace")
+    k_shadow = KERNEL_KINDS.index("shadow")
+    dom = k_trace if kernel_ms[k_trace] >= kernel_ms[k_shadow] else k_shadow
+    dom_bytes = (trace_bytes if dom == k_trace else shadow_bytes) / max(1, world)   # per rank share, approx. for N>1
+    dom_launches = max(1, kernel_launches[dom])
+    launches_per_step = dom_launches / args.steps
+    avg_launch_ms = kernel_ms[dom] / dom_launches
+    achieved = (dom_bytes / launches_per_step) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "reference assets (scenes/input: shotgun.obj + three 4096^2 maps), no randomness",
+        "config": {"workload": f"{args.scene}: 1920x1080 frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays,
+                   "l2": "flushed between timed frames (256 MiB write)", "partition": f"cyclic strips of {args.strip_rows} rows, 1 gather" if world > 1 else "single GPU",
+                   "timing": "CUDA events on the render stream per frame, summed; max over ranks"},
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "what": "rtb_render with a pinned host framebuffer (the Scene::render() call), wall clock"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_" + KERNEL_KINDS[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes / launches_per_step, "avg_launch_ms": avg_launch_ms,
+                     "launches_per_step": launches_per_step,
+                     "note": "bytes = 48/ray + 32/box test + 48/triangle test with the REFERENCE's work counts (SURVEY.md 8d); "
+                             "the scene is L2-resident, so this is a work-normalised yardstick, not DRAM traffic"},
+        "kernel_ms_per_step": {KERNEL_KINDS[k]: kernel_ms[k] / args.steps for k in range(len(KERNEL_KINDS))},
+        "clocks": sampler.summary(),
+    }
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            ms, info = run_reference(args.scene, 8, 1, rays)
+            info.pop("rays", None)
+            mean_ms = sum(ms) / len(ms)
+            line["cpu_baseline"] = dict(info, value=rays / (mean_ms * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=mean_ms)
+        except Exception as e:   # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

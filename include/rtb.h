@@ -135,15 +135,23 @@ typedef struct RtbScene {
     RtbImage  skybox[6];           /* left,front,right,back,top,bottom (scene.cpp:336-360)         */
 } RtbScene;
 
+/* kernel kinds for RtbStats.msKernel / launchesKernel */
+enum { RTB_K_RAYGEN = 0, RTB_K_TRACE = 1, RTB_K_SURFACE = 2, RTB_K_SHADOW = 3, RTB_K_SHADE = 4, RTB_K_COMBINE = 5,
+       RTB_K_SOBEL = 6, RTB_K_OUTPUT = 7, RTB_NKINDS = 8 };
+
 /* Work counters of one rtb_render call (64-bit: the reference's are int and wrap, stats.h:11-16). */
 typedef struct RtbStats {
     uint64_t rays;          /* Render::trace invocations: primary + secondary + shadow + SSAA     */
     uint64_t primaryRays, secondaryRays, shadowRays, ssaaPixels;
-    uint64_t boxTests;      /* only filled when the handle was created with RTB_CREATE_COUNTERS    */
-    uint64_t triTests;
+    uint64_t boxTests;      /* reference-walk box / triangle tests of ALL rays; only filled when   */
+    uint64_t triTests;      /* the handle was created with RTB_CREATE_COUNTERS                     */
+    uint64_t boxTestsShadow, triTestsShadow;      /* the shadow rays' share of the two above       */
+    uint64_t h2dBytes, d2hBytes;                  /* host<->device bytes copied inside the call    */
     uint32_t kernelLaunches;
     uint32_t levels;
     float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */
+    float    msKernel[RTB_NKINDS];                /* device time per kernel kind (CUDA events)     */
+    uint32_t launchesKernel[RTB_NKINDS];
 } RtbStats;
 
 typedef struct RtbHandle RtbHandle;

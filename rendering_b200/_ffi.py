@@ -65,11 +65,20 @@ class RtbScene(C.Structure):
 
 class RtbStats(C.Structure):
     _fields_ = [("rays", u64), ("primaryRays", u64), ("secondaryRays", u64), ("shadowRays", u64), ("ssaaPixels", u64),
-                ("boxTests", u64), ("triTests", u64), ("kernelLaunches", u32), ("levels", u32),
-                ("msPass1", f32), ("msSobel", f32), ("msSSAA", f32), ("msTotal", f32)]
+                ("boxTests", u64), ("triTests", u64), ("boxTestsShadow", u64), ("triTestsShadow", u64), ("h2dBytes", u64), ("d2hBytes", u64),
+                ("kernelLaunches", u32), ("levels", u32),
+                ("msPass1", f32), ("msSobel", f32), ("msSSAA", f32), ("msTotal", f32),
+                ("msKernel", f32 * 8), ("launchesKernel", u32 * 8)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {}
+        for n, _ in self._fields_:
+            v = getattr(self, n)
+            d[n] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+KERNEL_KINDS = ["raygen", "trace", "surface", "shadow", "shade", "combine", "sobel", "output"]
 
 
 # every symbol include/rtb.h declares, by library (tests check both lists against the header)

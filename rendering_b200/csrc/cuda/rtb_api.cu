@@ -87,6 +87,12 @@ struct RtbHandle {
     rtk::Counters* hCtr = nullptr;     // pinned
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 
+    // per-kernel timing: (kind, start, stop) spans recorded on the render stream, resolved at the end of a call
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> eventPool;
+    size_t eventsUsed = 0;
+
     // per-call bookkeeping
     int slotCount = 0;
     int interiorCount = 0;
@@ -141,6 +147,44 @@ int gridFor(const RtbHandle* h, long long n, int block = rtk::kBlock, int perSm 
 
 void launchCheck() { CK(cudaGetLastError()); }
 
+cudaEvent_t takeEvent(RtbHandle* h)
+{
+    if (h->eventsUsed == h->eventPool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->eventPool.push_back(e);
+    }
+    return h->eventPool[h->eventsUsed++];
+}
+
+// Brackets one kernel launch with CUDA events on the launching stream (RtbStats.msKernel).
+struct KernelSpan {
+    RtbHandle* h; cudaStream_t st; int kind; cudaEvent_t a, b;
+    KernelSpan(RtbHandle* h_, cudaStream_t st_, int kind_) : h(h_), st(st_), kind(kind_)
+    {
+        a = takeEvent(h); b = takeEvent(h);
+        CK(cudaEventRecord(a, st));
+    }
+    void done()
+    {
+        launchCheck();
+        CK(cudaEventRecord(b, st));
+        h->spans.push_back({ kind, a, b });
+        h->stats.kernelLaunches++;
+        h->stats.launchesKernel[kind]++;
+    }
+};
+
+void resolveSpans(RtbHandle* h)
+{
+    for (const auto& sp : h->spans) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) h->stats.msKernel[sp.kind] += ms;
+    }
+    h->spans.clear();
+    h->eventsUsed = 0;
+}
+
 // Makes room for a level of n rays: hit / surface / visibility records for n rays, up to 2n rays in
 // the other queue, up to n more interior records and 2n more colour slots.
 void reserveLevel(RtbHandle* h, cudaStream_t st, int cur, long long n)
@@ -179,6 +223,7 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
         h->hCtr->interiors = h->interiorCount;
         h->hCtr->slots = h->slotCount;
         CK(cudaMemcpyAsync(h->dCtr, h->hCtr, offsetof(rtk::Counters, ssaaPixels), cudaMemcpyHostToDevice, st));
+        h->stats.h2dBytes += offsetof(rtk::Counters, ssaaPixels);
 
         const rtk::RayQueue q = h->rays[cur].view(), next = h->rays[cur ^ 1].view();
         const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
@@ -187,26 +232,32 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
         const int interiorCap = (int)std::min<size_t>(h->interiors.bytes / sizeof(rtk::Interior), 1u << 30);
         const int slotCap = (int)std::min<size_t>(h->slots.bytes / (3 * sizeof(float)), 1u << 30);
 
-        if (count) rtk::k_trace<true><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
-        else rtk::k_trace<false><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
-        launchCheck();
-        rtk::k_surface<<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, surf, h->slots.as<float>(), h->dCtr);
-        launchCheck();
-        h->stats.kernelLaunches += 2;
+        {
+            KernelSpan ks(h, st, RTB_K_TRACE);
+            if (count) rtk::k_trace<true><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
+            else rtk::k_trace<false><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
+            ks.done();
+        }
+        {
+            KernelSpan ks(h, st, RTB_K_SURFACE);
+            rtk::k_surface<<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, surf, h->slots.as<float>(), h->dCtr);
+            ks.done();
+        }
         if (!(sc.flags & rt::FLAG_SHOW_NORMALS)) {
             if (sc.shadowRaysPerHit > 0) {
                 const long long maxShadow = n * sc.shadowRaysPerHit;
+                KernelSpan ks(h, st, RTB_K_SHADOW);
                 if (count) rtk::k_shadow<true><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
                 else rtk::k_shadow<false><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
-                launchCheck();
-                h->stats.kernelLaunches++;
+                ks.done();
             }
+            KernelSpan ks(h, st, RTB_K_SHADE);
             rtk::k_shade<<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, surf, h->vis.as<unsigned char>(), depth, next, nextCap,
                 h->interiors.as<rtk::Interior>(), interiorCap, h->slots.as<float>(), slotCap, h->dCtr);
-            launchCheck();
-            h->stats.kernelLaunches++;
+            ks.done();
         }
         CK(cudaMemcpyAsync(h->hCtr, h->dCtr, sizeof(rtk::Counters), cudaMemcpyDeviceToHost, st));
+        h->stats.d2hBytes += sizeof(rtk::Counters);
         CK(cudaStreamSynchronize(st));
         if (h->hCtr->overflow) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queue overflow" };
         h->stats.shadowRays += (uint64_t)h->hCtr->surfaces * (uint64_t)sc.shadowRaysPerHit;
@@ -220,9 +271,9 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
     for (int l = (int)levelRanges.size() - 1; l >= 0; --l) {
         const int first = levelRanges[l].first, last = levelRanges[l].second;
         if (last > first) {
+            KernelSpan ks(h, st, RTB_K_COMBINE);
             rtk::k_combine<<<gridFor(h, last - first), rtk::kBlock, 0, st>>>(h->interiors.as<rtk::Interior>(), first, last, h->slots.as<float>());
-            launchCheck();
-            h->stats.kernelLaunches++;
+            ks.done();
         }
     }
     // the queue holding level 0 must be queue 0 again for the next caller
@@ -233,6 +284,8 @@ void beginCall(RtbHandle* h)
 {
     CK(cudaSetDevice(h->device));
     h->stats = RtbStats{};
+    h->spans.clear();
+    h->eventsUsed = 0;
     h->slotCount = 0;
     h->interiorCount = 0;
     std::memset(h->hCtr, 0, sizeof(rtk::Counters));
@@ -268,6 +321,7 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
     h->rowsB.reserve(std::max<size_t>(1, owned.size()) * sizeof(int), st, false);
     CK(cudaMemcpyAsync(h->rowsA.p, p1rows.data(), p1rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->rowsB.p, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    h->stats.h2dBytes += (p1rows.size() + owned.size()) * sizeof(int);
 
     CK(cudaEventRecord(h->ev[0], st));
     h->slotCount = (int)framePixels;
@@ -278,9 +332,9 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
     const long long n0 = (long long)p1rows.size() * (w - 1);
     if (n0 > 0) {
         reserveLevel(h, st, 0, n0);
+        KernelSpan ks(h, st, RTB_K_RAYGEN);
         rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)p1rows.size(), h->rays[0].view());
-        launchCheck();
-        h->stats.kernelLaunches++;
+        ks.done();
         runLevels(h, st, n0, h->stats.primaryRays);
     }
     CK(cudaEventRecord(h->ev[1], st));
@@ -293,21 +347,27 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
             h->outStage.reserve(outFloats * sizeof(float), st, false);
             target = h->outStage.as<float>();
         }
+        KernelSpan ks(h, st, RTB_K_OUTPUT);
         rtk::k_gather_rows<<<gridFor(h, (long long)outFloats), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(), (int)owned.size(), target);
-        launchCheck();
-        h->stats.kernelLaunches++;
-        if (!fbOnDevice) CK(cudaMemcpyAsync(dst, target, outFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
+        ks.done();
+        if (!fbOnDevice) {
+            CK(cudaMemcpyAsync(dst, target, outFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
+            h->stats.d2hBytes += outFloats * sizeof(float);
+        }
     };
     if (pass1) { emit(pass1); if (!fbOnDevice) CK(cudaStreamSynchronize(st)); }
 
     int nFlagged = 0;
     if ((sc.flags & rt::FLAG_SSAA) && !owned.empty()) {
         h->flagged.reserve(owned.size() * (size_t)w * sizeof(int), st, false);
-        rtk::k_sobel<<<gridFor(h, (long long)owned.size() * w), rtk::kBlock, 0, st>>>(w, ht, h->slots.as<float>(), h->rowsB.as<int>(),
-            (int)owned.size(), h->flagged.as<int>(), h->dCtr);
-        launchCheck();
-        h->stats.kernelLaunches++;
+        {
+            KernelSpan ks(h, st, RTB_K_SOBEL);
+            rtk::k_sobel<<<gridFor(h, (long long)owned.size() * w), rtk::kBlock, 0, st>>>(w, ht, h->slots.as<float>(), h->rowsB.as<int>(),
+                (int)owned.size(), h->flagged.as<int>(), h->dCtr);
+            ks.done();
+        }
         CK(cudaMemcpyAsync(h->hCtr, h->dCtr, sizeof(rtk::Counters), cudaMemcpyDeviceToHost, st));
+        h->stats.d2hBytes += sizeof(rtk::Counters);
         CK(cudaEventRecord(h->ev[2], st));
         CK(cudaStreamSynchronize(st));
         nFlagged = h->hCtr->ssaaPixels;
@@ -317,13 +377,15 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
             const int slotBase = h->slotCount;
             h->slotCount += (int)n1;
             reserveLevel(h, st, 0, n1);
-            rtk::k_ssaa_gen<<<gridFor(h, n1), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), nFlagged, slotBase, h->rays[0].view());
-            launchCheck();
-            h->stats.kernelLaunches++;
+            {
+                KernelSpan ks(h, st, RTB_K_RAYGEN);
+                rtk::k_ssaa_gen<<<gridFor(h, n1), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), nFlagged, slotBase, h->rays[0].view());
+                ks.done();
+            }
             runLevels(h, st, n1, h->stats.primaryRays);
+            KernelSpan ks(h, st, RTB_K_OUTPUT);
             rtk::k_ssaa_resolve<<<gridFor(h, nFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), nFlagged, slotBase, h->slots.as<float>());
-            launchCheck();
-            h->stats.kernelLaunches++;
+            ks.done();
         }
     } else {
         CK(cudaEventRecord(h->ev[2], st));
@@ -334,9 +396,12 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
 
     if (h->createFlags & RTB_CREATE_COUNTERS) {
         CK(cudaMemcpy(h->hCtr, h->dCtr, sizeof(rtk::Counters), cudaMemcpyDeviceToHost));
-        h->stats.boxTests = h->hCtr->boxTests;
-        h->stats.triTests = h->hCtr->triTests;
+        h->stats.boxTestsShadow = h->hCtr->boxTestsShadow;
+        h->stats.triTestsShadow = h->hCtr->triTestsShadow;
+        h->stats.boxTests = h->hCtr->boxTests + h->hCtr->boxTestsShadow;
+        h->stats.triTests = h->hCtr->triTests + h->hCtr->triTestsShadow;
     }
+    resolveSpans(h);
     h->stats.rays = h->stats.primaryRays + h->stats.secondaryRays + h->stats.shadowRays;
     h->stats.msPass1 = elapsed(h->ev[0], h->ev[1]);
     h->stats.msSobel = elapsed(h->ev[1], h->ev[2]);
@@ -385,6 +450,7 @@ void destroyHandle(RtbHandle* h)
     if (h->dCtr) cudaFree(h->dCtr);
     if (h->hCtr) cudaFreeHost(h->hCtr);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->eventPool) cudaEventDestroy(e);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
     delete h;
 }

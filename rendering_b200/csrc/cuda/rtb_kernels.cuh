@@ -39,7 +39,8 @@ struct Counters {
     int slots;           // colour slots handed out
     int ssaaPixels;      // pixels flagged by k_sobel
     int overflow;        // set when a queue would overflow its capacity
-    unsigned long long boxTests, triTests;
+    unsigned long long boxTests, triTests;            // closest-hit rays (k_trace)
+    unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (k_shadow)
 };
 
 // Structure-of-arrays ray queue (one level).
@@ -299,8 +300,8 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, SurfQueue surf, uns
         vis[qi] = blocked ? 0 : 1;
     }
     if (COUNT) {
-        atomicAdd(&ctr->boxTests, nBox);
-        atomicAdd(&ctr->triTests, nTri);
+        atomicAdd(&ctr->boxTestsShadow, nBox);
+        atomicAdd(&ctr->triTestsShadow, nTri);
     }
 }
 

@@ -1,0 +1,50 @@
+"""Host-side multi-GPU logic on CPU: the cyclic strip partition and the one-collective frame
+gather, with world_size 2 and 3 over gloo."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rendering_b200 import _ffi
+from rendering_b200 import dist as rdist
+
+
+def test_partition_matches_c_abi_and_covers_every_row_once():
+    lib = C.CDLL(_ffi.CUDA_LIB_PATH)
+    lib.rtb_strip_rows_owned.restype = C.c_int
+    for height, strip, world in [(1080, 8, 8), (1080, 32, 4), (256, 8, 3), (7, 8, 2), (92, 5, 8)]:
+        seen = np.zeros(height, int)
+        for r in range(world):
+            rows = rdist.owned_rows(height, strip, r, world)
+            assert len(rows) == lib.rtb_strip_rows_owned(height, strip, r, world)
+            seen[rows] += 1
+        assert (seen == 1).all()
+    assert lib.rtb_strip_rows_owned(100, 0, 0, 2) < 0     # bad arguments are refused
+
+
+def _worker(rank, world, port, height, width, strip, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(height * width * 3, dtype=torch.float32).reshape(height, width, 3)
+    rows = rdist.owned_rows(height, strip, rank, world)
+    local = torch.full((rdist.max_rows(height, strip, world), width, 3), -1.0)
+    local[: len(rows)] = full[torch.as_tensor(rows)]          # what rtb_render_strips would have produced
+    frame = rdist.gather_frame(local, height, strip, rank, world)
+    if rank == 0:
+        assert frame is not None and torch.equal(frame, full)
+        open(os.path.join(out_dir, "ok"), "w").write("1")
+    else:
+        assert frame is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height,strip", [(2, 37, 8), (3, 50, 4)])
+def test_gather_frame_gloo(tmp_path, world, height, strip):
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, height, 16, strip, str(tmp_path)), nprocs=world, join=True)
+    assert (tmp_path / "ok").exists()
