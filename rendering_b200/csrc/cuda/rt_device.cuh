@@ -18,6 +18,9 @@
 #define RT_HD __host__ __device__ __forceinline__
 #else
 #define RT_HD inline
+// plain-C++ stand-ins for the CUDA vector types (tests/shim compiles this header with g++)
+struct float4 { float x, y, z, w; };
+struct int2 { int x, y; };
 #endif
 
 namespace rt {
@@ -106,6 +109,12 @@ struct Mesh {
     const float* tan;   // 6 per triangle
     Image diffuse, normal, specular;
     int nNodes, nSlots, nTris, maxDepth;
+    // fast path (bvh_build.h): search BVH over unique triangles + eligibility tables
+    const float4* bvhNodes;    // 4 x float4 per node
+    const float4* bvhTris;     // 3 x float4 per triangle, BVH leaf order
+    const int* triRefOff;      // nTris+1: range of a triangle's references in triRefs
+    const int2* triRefs;       // (reference-tree leaf node, reference slot), ascending slot
+    const int* parent;         // reference-tree parent of every node, -1 at the root
 };
 
 struct Scene {
@@ -193,6 +202,25 @@ RT_HD bool lineHitsBox(const RayCtx& r, float lox, float loy, float loz, float h
     if (tymax < tmax) tmax = tymax;
     const float tzmin = ((r.sz ? hiz : loz) - r.o.z) * r.inv.z;
     const float tzmax = ((r.sz ? loz : hiz) - r.o.z) * r.inv.z;
+    if ((tmin > tzmax) || (tzmin > tmax)) return false;
+    return true;
+}
+
+// Same test, additionally reporting whether any slab product was NaN (0 * inf: a zero direction
+// component with the origin exactly on a box plane).  NaNs make the reference's comparisons
+// vacuous, which is the only way a child box can pass while an ancestor fails.
+RT_HD bool lineHitsBoxNaN(const RayCtx& r, float lox, float loy, float loz, float hix, float hiy, float hiz, bool& sawNaN)
+{
+    float tmin = ((r.sx ? hix : lox) - r.o.x) * r.inv.x;
+    float tmax = ((r.sx ? lox : hix) - r.o.x) * r.inv.x;
+    const float tymin = ((r.sy ? hiy : loy) - r.o.y) * r.inv.y;
+    const float tymax = ((r.sy ? loy : hiy) - r.o.y) * r.inv.y;
+    const float tzmin = ((r.sz ? hiz : loz) - r.o.z) * r.inv.z;
+    const float tzmax = ((r.sz ? loz : hiz) - r.o.z) * r.inv.z;
+    sawNaN = (tmin != tmin) | (tmax != tmax) | (tymin != tymin) | (tymax != tymax) | (tzmin != tzmin) | (tzmax != tzmax);
+    if ((tmin > tymax) || (tymin > tmax)) return false;
+    if (tymin > tmin) tmin = tymin;
+    if (tymax < tmax) tmax = tymax;
     if ((tmin > tzmax) || (tzmin > tmax)) return false;
     return true;
 }
@@ -428,5 +456,118 @@ RT_HD float fresnel(V3 dir, V3 n, float ior)   // scene.cpp:698-722
 // std::pow(float,float) == glibc powf, which is correctly rounded in all but vanishingly rare
 // cases; CUDA's powf is only good to a few ulp, so evaluate in double and round once.
 RT_HD float powExact(float x, float y) { return (float)pow((double)x, (double)y); }
+
+#if defined(__CUDA_ARCH__)
+#define RT_LDG(p) __ldg(p)
+#else
+#define RT_LDG(p) (*(p))
+#endif
+RT_HD int floatBits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    union { float f; int i; } c; c.f = f; return c.i;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast path: search BVH + exact eligibility
+// ------------------------------------------------------------------------------------------------
+// What the reference tree computes for a ray is: among all (leaf, triangle) references whose leaf is
+// ELIGIBLE — the ray line passes lineHitsBox for the leaf and every ancestor — the hit with the
+// smallest t, ties going to the smallest reference slot (DFS order, strict `<`).  Boxes are nested
+// (children are the parent cut at a plane) and the slab arithmetic is monotone, so a leaf that
+// passes WITHOUT producing a NaN implies all its ancestors pass; only NaN cases walk the parents.
+// Returns the smallest eligible reference slot of triangle `tri`, or -1.
+RT_HD int eligibleSlot(const Scene& sc, const Mesh& me, const RayCtx& r, int tri)
+{
+    const int b = RT_LDG(me.triRefOff + tri), e = RT_LDG(me.triRefOff + tri + 1);
+    if (!(sc.flags & FLAG_USE_AC)) return b < e ? RT_LDG(me.triRefs + b).y : -1;
+    const float4* nodes = reinterpret_cast<const float4*>(me.nodes);
+    for (int i = b; i < e; ++i) {
+        const int2 ref = RT_LDG(me.triRefs + i);
+        const float4 n0 = RT_LDG(nodes + 2 * ref.x), n1 = RT_LDG(nodes + 2 * ref.x + 1);
+        bool nan;
+        if (!lineHitsBoxNaN(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, nan)) continue;
+        bool ok = true;
+        if (nan) {
+            for (int p = RT_LDG(me.parent + ref.x); p >= 0; p = RT_LDG(me.parent + p)) {
+                const float4 a0 = RT_LDG(nodes + 2 * p), a1 = RT_LDG(nodes + 2 * p + 1);
+                if (!lineHitsBox(r, a0.x, a0.y, a0.z, a0.w, a1.x, a1.y)) { ok = false; break; }
+            }
+        }
+        if (ok) return ref.y;
+    }
+    return -1;
+}
+
+// conservative ray-segment / padded-box test for CULLING only (never decides a hit): NaN-ignoring
+// min/max keep a NaN axis from rejecting
+RT_HD float slabEntry(const RayCtx& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float tFar, bool& hit)
+{
+    const float t0x = (lox - r.o.x) * r.inv.x, t1x = (hix - r.o.x) * r.inv.x;
+    const float t0y = (loy - r.o.y) * r.inv.y, t1y = (hiy - r.o.y) * r.inv.y;
+    const float t0z = (loz - r.o.z) * r.inv.z, t1z = (hiz - r.o.z) * r.inv.z;
+    const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tFar));
+    hit = tn <= tf;
+    return tn;
+}
+
+// Closest hit (ANY = false) or occlusion test against tLimit (ANY = true) of one mesh.
+template <bool ANY>
+RT_HD bool walkMeshFast(const Scene& sc, const Mesh& me, const RayCtx& r, int* stack, int stackStride, float tLimit,
+    float& tBest, float& uBest, float& vBest, int& triBest)
+{
+    if (me.nNodes == 0) return false;
+    const bool cull = sc.flags & FLAG_CULL;
+    bool found = false;
+    int slotBest = 0x7fffffff;
+    int sp = 0;
+    int cur = 0;   // >= 0 inner node, < 0 leaf
+    for (;;) {
+        if (cur >= 0) {
+            const float4* nd = me.bvhNodes + (size_t)cur * 4;
+            const float4 a = RT_LDG(nd), b = RT_LDG(nd + 1), c = RT_LDG(nd + 2), d = RT_LDG(nd + 3);
+            const float tFar = ANY ? tLimit : tBest;
+            bool h0, h1;
+            const float e0 = slabEntry(r, a.x, a.y, a.z, a.w, b.x, b.y, tFar, h0);
+            const float e1 = slabEntry(r, b.z, b.w, c.x, c.y, c.z, c.w, tFar, h1);
+            const int c0 = floatBits(d.x), c1 = floatBits(d.y);
+            if (h0 && h1) {
+                const bool swap = e1 < e0;
+                stack[sp * stackStride] = swap ? c0 : c1;
+                sp++;
+                cur = swap ? c1 : c0;
+                continue;
+            }
+            if (h0) { cur = c0; continue; }
+            if (h1) { cur = c1; continue; }
+        } else {
+            const int code = ~cur;
+            const int first = code >> 3, count = (code & 7) + 1;
+            const float4* tp = me.bvhTris + (size_t)first * 3;
+            for (int k = 0; k < count; ++k, tp += 3) {
+                const float4 p0 = RT_LDG(tp), p1 = RT_LDG(tp + 1), p2 = RT_LDG(tp + 2);
+                float t, u, v;
+                if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
+                const int tri = floatBits(p0.w);
+                if (ANY) {
+                    if (t < tLimit && eligibleSlot(sc, me, r, tri) >= 0) return true;
+                } else if (t < tBest || (found && t == tBest)) {
+                    const int slot = eligibleSlot(sc, me, r, tri);
+                    if (slot >= 0 && (t < tBest || slot < slotBest)) {
+                        tBest = t; uBest = u; vBest = v; triBest = tri; slotBest = slot; found = true;
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        sp--;
+        cur = stack[sp * stackStride];
+    }
+    return found;
+}
 
 } // namespace rt

@@ -9,6 +9,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -138,6 +140,20 @@ rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
     return out;
 }
 
+// Fast-path data of one mesh: search BVH over its unique triangles (bvh_build.h) and the tables that
+// let the kernel evaluate the reference tree's eligibility rule for a single triangle.
+void buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
+{
+    rtpack::FastPath fp;
+    rtpack::packFastPath(m, fp);
+    if (fp.maxDepth > rtk::kStackDepth) throw std::runtime_error("search BVH deeper than the traversal stack (64)");
+    d.bvhNodes = reinterpret_cast<const float4*>(upload(h, fp.nodes.data(), fp.nodes.size()));
+    d.bvhTris = upload(h, fp.tris.data(), fp.tris.size());
+    d.triRefOff = upload(h, fp.triRefOff.data(), fp.triRefOff.size());
+    d.triRefs = upload(h, fp.triRefs.data(), fp.triRefs.size());
+    d.parent = upload(h, fp.parent.data(), fp.parent.size());
+}
+
 int gridFor(const RtbHandle* h, long long n, int block = rtk::kBlock, int perSm = 16)
 {
     const long long blocks = (n + block - 1) / block;
@@ -207,6 +223,7 @@ void reserveLevel(RtbHandle* h, cudaStream_t st, int cur, long long n)
 void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirstLevel)
 {
     const bool count = h->createFlags & RTB_CREATE_COUNTERS;
+    const bool exact = h->createFlags & RTB_CREATE_EXACT_WALK;
     const rt::Scene& sc = h->scene;
     std::vector<std::pair<int, int>> levelRanges;
     int cur = 0;
@@ -234,8 +251,9 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
 
         {
             KernelSpan ks(h, st, RTB_K_TRACE);
-            if (count) rtk::k_trace<true><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
-            else rtk::k_trace<false><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
+            if (count) rtk::k_trace<rtk::MODE_COUNT><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
+            else if (exact) rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
+            else rtk::k_trace<rtk::MODE_FAST><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
             ks.done();
         }
         {
@@ -247,8 +265,9 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
             if (sc.shadowRaysPerHit > 0) {
                 const long long maxShadow = n * sc.shadowRaysPerHit;
                 KernelSpan ks(h, st, RTB_K_SHADOW);
-                if (count) rtk::k_shadow<true><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
-                else rtk::k_shadow<false><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
+                if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
+                else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
+                else rtk::k_shadow<rtk::MODE_FAST><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
                 ks.done();
             }
             KernelSpan ks(h, st, RTB_K_SHADE);
@@ -506,6 +525,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             d.normal = uploadImage(h, m.normalMap);
             d.specular = uploadImage(h, m.specularMap);
             d.nNodes = m.nNodes; d.nSlots = m.nRefs; d.nTris = m.nTris; d.maxDepth = pm.maxDepth;
+            if (m.nNodes > 0) buildFastPath(h, m, d);
             meshes.push_back(d);
         }
         h->scene.objects = upload(h, objects.data(), objects.size());
@@ -564,7 +584,10 @@ int rtb_trace(RtbHandle* h, const float* rays, int nRays, float* tuv, int32_t* o
         rtk::k_rays_from_user<<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->userRays.as<float>(), nRays, 0, h->rays[0].view());
         launchCheck();
         const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
-        rtk::k_trace<false><<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dCtr);
+        if (h->createFlags & (RTB_CREATE_EXACT_WALK | RTB_CREATE_COUNTERS))
+            rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dCtr);
+        else
+            rtk::k_trace<rtk::MODE_FAST><<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dCtr);
         launchCheck();
         std::vector<float4> t4(nRays);
         std::vector<int> ob(nRays);

@@ -174,8 +174,10 @@ __device__ __forceinline__ bool walkMesh(const Scene& sc, const Mesh& me, const 
     return found;
 }
 
+enum { MODE_FAST = 0, MODE_EXACT = 1, MODE_COUNT = 2 };
+
 // Render::trace for primary / secondary rays (scene.cpp:724-756)
-template <bool COUNT>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int n, HitQueue hits, Counters* ctr)
 {
     __shared__ int stackMem[kStackDepth * kBlock];
@@ -191,15 +193,17 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int n, H
             float t = FLT_MAX, u = 0.0f, v = 0.0f;
             int tri = -1;
             bool ok;
-            if (ob.type == OBJ_MESH) ok = walkMesh<false, COUNT>(sc, sc.meshes[ob.mesh], r, stack, 0.0f, t, u, v, tri, nBox, nTri);
-            else if (ob.type == OBJ_SPHERE) ok = hitSphere(r, ob.pos, ob.r2, t);
+            if (ob.type == OBJ_MESH) {
+                if (MODE == MODE_FAST) ok = walkMeshFast<false>(sc, sc.meshes[ob.mesh], r, stack, kBlock, 0.0f, t, u, v, tri);
+                else ok = walkMesh<false, MODE == MODE_COUNT>(sc, sc.meshes[ob.mesh], r, stack, 0.0f, t, u, v, tri, nBox, nTri);
+            } else if (ob.type == OBJ_SPHERE) ok = hitSphere(r, ob.pos, ob.r2, t);
             else ok = hitPlane(r, ob.pos, ob.normal, t);
             if (ok && t < tNear) { tNear = t; uN = u; vN = v; objN = k; triN = tri; }
         }
         hits.tuv[i] = make_float4(tNear, uN, vN, __int_as_float(triN));
         hits.obj[i] = objN;
     }
-    if (COUNT) {
+    if (MODE == MODE_COUNT) {
         atomicAdd(&ctr->boxTests, nBox);
         atomicAdd(&ctr->triTests, nTri);
     }
@@ -262,7 +266,7 @@ __device__ __forceinline__ void shadowSample(const Scene& sc, int k, V3 P, V3& L
 
 // Shadow trace (scene.cpp:787 etc.): Transparent objects cast no shadow (:733); an occluder counts
 // only when it is closer than the light (`tNear < intrInfo.tNear`, tNear preloaded by illuminate).
-template <bool COUNT>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, SurfQueue surf, unsigned char* __restrict__ vis, Counters* ctr)
 {
     __shared__ int stackMem[kStackDepth * kBlock];
@@ -285,21 +289,22 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, SurfQueue surf, uns
             float t = FLT_MAX, u, v; int tri;
             bool ok;
             if (ob.type == OBJ_MESH) {
-                if (COUNT) {
+                if (MODE == MODE_COUNT) {
                     // full closest-hit walk so the work counters equal the reference's
                     ok = walkMesh<false, true>(sc, sc.meshes[ob.mesh], r, stack, 0.0f, t, u, v, tri, nBox, nTri);
                 } else {
-                    ok = walkMesh<true, false>(sc, sc.meshes[ob.mesh], r, stack, tNear, t, u, v, tri, nBox, nTri);
+                    if (MODE == MODE_FAST) ok = walkMeshFast<true>(sc, sc.meshes[ob.mesh], r, stack, kBlock, tNear, t, u, v, tri);
+                    else ok = walkMesh<true, false>(sc, sc.meshes[ob.mesh], r, stack, tNear, t, u, v, tri, nBox, nTri);
                     if (ok) { blocked = true; break; }
                     continue;
                 }
             } else if (ob.type == OBJ_SPHERE) ok = hitSphere(r, ob.pos, ob.r2, t);
             else ok = hitPlane(r, ob.pos, ob.normal, t);
-            if (ok && t < tNear) { tNear = t; blocked = true; if (!COUNT) break; }
+            if (ok && t < tNear) { tNear = t; blocked = true; if (MODE != MODE_COUNT) break; }
         }
         vis[qi] = blocked ? 0 : 1;
     }
-    if (COUNT) {
+    if (MODE == MODE_COUNT) {
         atomicAdd(&ctr->boxTestsShadow, nBox);
         atomicAdd(&ctr->triTestsShadow, nTri);
     }

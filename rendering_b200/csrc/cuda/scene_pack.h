@@ -4,10 +4,13 @@
 #pragma once
 
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
 #include "../../../include/rtb.h"
+#include "bvh_build.h"
 #include "rt_device.cuh"
 
 namespace rtpack {
@@ -41,6 +44,64 @@ inline void packMesh(const RtbMesh& m, PackedMesh& out)
         d.tri = tri;
         d.e1x = p[3] - p[0]; d.e1y = p[4] - p[1]; d.e1z = p[5] - p[2];   // v1 - v0 (objects.cpp:70)
         d.e2x = p[6] - p[0]; d.e2y = p[7] - p[1]; d.e2z = p[8] - p[2];   // v2 - v0 (objects.cpp:71)
+    }
+}
+
+// Fast-path tables of one mesh (see rt_device.cuh walkMeshFast / eligibleSlot).
+struct FastPath {
+    std::vector<rtbvh::Node> nodes;
+    std::vector<float4> tris;        // 3 per triangle, BVH leaf order
+    std::vector<int> triRefOff;      // nTris + 1
+    std::vector<int2> triRefs;       // (reference leaf node, slot), ascending slot per triangle
+    std::vector<int> parent;         // reference-tree parents
+    int maxDepth = 0;
+    float pad = 0;
+};
+
+inline void packFastPath(const RtbMesh& m, FastPath& out)
+{
+    // padding: a hit accepted by the float Moller-Trumbore test lies within rounding distance of the
+    // triangle; 1e-4 of the mesh diagonal is orders of magnitude above that
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    for (size_t i = 0; i < (size_t)m.nTris * 3; ++i)
+        for (int a = 0; a < 3; ++a) {
+            const float v = m.pos[i * 3 + a];
+            if (v >= -FLT_MAX && v <= FLT_MAX) { lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+        }
+    double diag2 = 0;
+    for (int a = 0; a < 3; ++a) diag2 += hi[a] > lo[a] ? (double)(hi[a] - lo[a]) * (hi[a] - lo[a]) : 0.0;
+    out.pad = (float)(1e-4 * std::sqrt(diag2)) + 1e-7f;
+
+    rtbvh::Builder builder;
+    rtbvh::Result bvh = builder.build(m.pos, m.nTris, out.pad);
+    out.maxDepth = bvh.maxDepth;
+    out.nodes.swap(bvh.nodes);
+    out.tris.resize(bvh.triOrder.size() * 3);
+    for (size_t k = 0; k < bvh.triOrder.size(); ++k) {
+        const int tri = bvh.triOrder[k];
+        const float* p = m.pos + (size_t)tri * 9;
+        float triAsFloat;
+        std::memcpy(&triAsFloat, &tri, 4);
+        out.tris[k * 3 + 0] = float4{ p[0], p[1], p[2], triAsFloat };
+        out.tris[k * 3 + 1] = float4{ p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f };   // v1 - v0 (objects.cpp:70)
+        out.tris[k * 3 + 2] = float4{ p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f };   // v2 - v0 (objects.cpp:71)
+    }
+
+    out.parent.assign(m.nNodes, -1);
+    std::vector<int>& off = out.triRefOff;
+    off.assign(m.nTris + 1, 0);
+    for (int k = 0; k < m.nNodes; ++k) {
+        const RtbNode& n = m.nodes[k];
+        if (n.right >= 0) { out.parent[k + 1] = k; out.parent[n.right] = k; }
+        else for (int s = n.firstRef; s < n.firstRef + n.refCount; ++s) off[m.refs[s] + 1]++;
+    }
+    for (int t = 0; t < m.nTris; ++t) off[t + 1] += off[t];
+    out.triRefs.resize(m.nRefs);
+    std::vector<int> cursor(off.begin(), off.end() - 1);
+    for (int k = 0; k < m.nNodes; ++k) {   // pre-order: leaves, hence slots, in ascending DFS order
+        const RtbNode& n = m.nodes[k];
+        if (n.right >= 0) continue;
+        for (int s = n.firstRef; s < n.firstRef + n.refCount; ++s) out.triRefs[cursor[m.refs[s]]++] = int2{ k, s };
     }
 }
 

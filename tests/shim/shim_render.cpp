@@ -22,6 +22,8 @@ struct HostScene {
     std::vector<Mesh> meshes;
     std::vector<rtpack::PackedMesh> packed;
     std::vector<std::vector<unsigned char>> images;
+    std::vector<rtpack::FastPath> fast;
+    bool useFast = false;
     unsigned long long rays = 0, boxTests = 0, triTests = 0;
 };
 
@@ -49,6 +51,14 @@ bool traceRay(HostScene& hs, V3 o, V3 d, bool shadow, float tMax, Hit& hit)
         if (ob.type == OBJ_MESH) {
             const Mesh& me = sc.meshes[ob.mesh];
             if (me.nNodes == 0) continue;
+            if (hs.useFast) {
+                int fstack[128];
+                if (shadow) ok = walkMeshFast<true>(sc, me, r, fstack, 1, tMax, t, u, v, tri);
+                else ok = walkMeshFast<false>(sc, me, r, fstack, 1, 0.0f, t, u, v, tri);
+                if (ok && shadow) { hit.obj = k; return true; }
+                if (ok && t < hit.t) { hit.t = t; hit.u = u; hit.v = v; hit.obj = k; hit.tri = tri; }
+                continue;
+            }
             int stack[128]; int sp = 0; int node = 0;
             for (;;) {
                 const Node& n = me.nodes[node];
@@ -149,9 +159,19 @@ extern "C" {
 
 // Renders the whole frame on the CPU with the backend's device arithmetic.  pass1/final: h*w*3.
 // counters: {rays, boxTests, triTests, ssaaPixels}
-int shim_render(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4])
+static int render_impl(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4], bool fast);
+
+int shim_render(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4]) { return render_impl(s, pass1, final, counters, false); }
+// same, but meshes are searched through the fast path (search BVH + eligibility tables)
+int shim_render_fast(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4]) { return render_impl(s, pass1, final, counters, true); }
+
+} // extern "C"
+
+static int render_impl(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4], bool fast)
 {
     HostScene hs;
+    hs.useFast = fast;
+    hs.fast.resize(s->nMeshes);
     rtpack::packHeader(*s, hs.sc);
     hs.images.reserve(64);
     for (int i = 0; i < s->nObjects; ++i) hs.objects.push_back(rtpack::packObject(s->objects[i]));
@@ -167,6 +187,14 @@ int shim_render(const RtbScene* s, float* pass1, float* final, unsigned long lon
         m.specular = hostImage(hs, s->meshes[i].specularMap);
         m.nNodes = s->meshes[i].nNodes; m.nSlots = s->meshes[i].nRefs; m.nTris = s->meshes[i].nTris;
         m.maxDepth = hs.packed[i].maxDepth;
+        if (fast && m.nNodes > 0) {
+            rtpack::packFastPath(s->meshes[i], hs.fast[i]);
+            m.bvhNodes = reinterpret_cast<const float4*>(hs.fast[i].nodes.data());
+            m.bvhTris = hs.fast[i].tris.data();
+            m.triRefOff = hs.fast[i].triRefOff.data();
+            m.triRefs = hs.fast[i].triRefs.data();
+            m.parent = hs.fast[i].parent.data();
+        }
         hs.meshes.push_back(m);
     }
     for (int k = 0; k < 6; ++k) hs.sc.sky[k] = hostImage(hs, s->skybox[k]);
@@ -219,4 +247,4 @@ int shim_render(const RtbScene* s, float* pass1, float* final, unsigned long lon
     return 0;
 }
 
-} // extern "C"
+

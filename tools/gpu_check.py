@@ -53,6 +53,14 @@ def main():
         fb, p1, st = r.render(want_pass1=True)
         res["stats_counted"] = st
         r.close()
+        r = rb.Renderer(sc, exact_walk=True)
+        times = []
+        for _ in range(reps):
+            fbx, stx = r.render()
+            times.append(stx["msTotal"])
+        res["ms_total_exact_walk"] = times
+        res["exact_same_as_counted"] = bool((fbx.view(np.uint32) == fb.view(np.uint32)).all())
+        r.close()
         r = rb.Renderer(sc)
         times = []
         for _ in range(reps):
@@ -60,7 +68,9 @@ def main():
             times.append(st2["msTotal"])
         res["ms_total"] = times
         res["stats"] = st2
-        res["same_as_counted"] = bool((fb2.view(np.uint32) == fb.view(np.uint32)).all())
+        res["kernel_ms"] = dict(zip(rb._ffi.KERNEL_KINDS, st2["msKernel"]))
+        res["fast_same_as_counted"] = bool((fb2.view(np.uint32) == fb.view(np.uint32)).all())
+        res["fast_pixels_differing"] = int((fb2.view(np.uint32) != fb.view(np.uint32)).any(axis=2).sum())
         if use_ref:
             prefix, info = ref_render(cfg, tmp)
             res["ref"] = info
