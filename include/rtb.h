@@ -147,6 +147,8 @@ typedef struct RtbStats {
     uint64_t triTests;      /* the handle was created with RTB_CREATE_COUNTERS                     */
     uint64_t boxTestsShadow, triTestsShadow;      /* the shadow rays' share of the two above       */
     uint64_t h2dBytes, d2hBytes;                  /* host<->device bytes copied inside the call    */
+    uint64_t shadowRaysSkipped;   /* shadow rays (counted in `rays`) whose visibility cannot affect the pixel
+                                     and that the fast path therefore does not trace                      */
     uint32_t kernelLaunches;
     uint32_t levels;
     float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */

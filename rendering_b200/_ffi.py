@@ -65,7 +65,7 @@ class RtbScene(C.Structure):
 
 class RtbStats(C.Structure):
     _fields_ = [("rays", u64), ("primaryRays", u64), ("secondaryRays", u64), ("shadowRays", u64), ("ssaaPixels", u64),
-                ("boxTests", u64), ("triTests", u64), ("boxTestsShadow", u64), ("triTestsShadow", u64), ("h2dBytes", u64), ("d2hBytes", u64),
+                ("boxTests", u64), ("triTests", u64), ("boxTestsShadow", u64), ("triTestsShadow", u64), ("h2dBytes", u64), ("d2hBytes", u64), ("shadowRaysSkipped", u64),
                 ("kernelLaunches", u32), ("levels", u32),
                 ("msPass1", f32), ("msSobel", f32), ("msSSAA", f32), ("msTotal", f32),
                 ("msKernel", f32 * 8), ("launchesKernel", u32 * 8)]

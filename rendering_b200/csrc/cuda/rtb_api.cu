@@ -161,6 +161,14 @@ int gridFor(const RtbHandle* h, long long n, int block = rtk::kBlock, int perSm 
     return (int)std::max(1LL, std::min(blocks, cap));
 }
 
+// persistent kernels: one resident wave (6 CTAs of 128 threads per SM with the 32 KiB stack), never more
+// CTAs than there is work for
+int persistentGrid(const RtbHandle* h, long long n)
+{
+    const long long blocks = (n + rtk::kBlock - 1) / rtk::kBlock;
+    return (int)std::max(1LL, std::min(blocks, (long long)h->smCount * 6));
+}
+
 void launchCheck() { CK(cudaGetLastError()); }
 
 cudaEvent_t takeEvent(RtbHandle* h)
@@ -253,7 +261,10 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
             KernelSpan ks(h, st, RTB_K_TRACE);
             if (count) rtk::k_trace<rtk::MODE_COUNT><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
             else if (exact) rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
-            else rtk::k_trace<rtk::MODE_FAST><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
+            else {
+                CK(cudaMemsetAsync(&h->dCtr->walkCursor[0], 0, 2 * sizeof(unsigned long long), st));
+                rtk::k_walk<false><<<persistentGrid(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, surf, h->vis.as<unsigned char>(), h->dCtr, &h->dCtr->walkCursor[0]);
+            }
             ks.done();
         }
         {
@@ -265,9 +276,9 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
             if (sc.shadowRaysPerHit > 0) {
                 const long long maxShadow = n * sc.shadowRaysPerHit;
                 KernelSpan ks(h, st, RTB_K_SHADOW);
-                if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
-                else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
-                else rtk::k_shadow<rtk::MODE_FAST><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, surf, h->vis.as<unsigned char>(), h->dCtr);
+                if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, q, surf, h->vis.as<unsigned char>(), h->dCtr);
+                else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, q, surf, h->vis.as<unsigned char>(), h->dCtr);
+                else rtk::k_walk<true><<<persistentGrid(h, maxShadow), rtk::kBlock, 0, st>>>(sc, q, 0, hits, surf, h->vis.as<unsigned char>(), h->dCtr, &h->dCtr->walkCursor[1]);
                 ks.done();
             }
             KernelSpan ks(h, st, RTB_K_SHADE);
@@ -280,6 +291,7 @@ void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirs
         CK(cudaStreamSynchronize(st));
         if (h->hCtr->overflow) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queue overflow" };
         h->stats.shadowRays += (uint64_t)h->hCtr->surfaces * (uint64_t)sc.shadowRaysPerHit;
+        h->stats.shadowRaysSkipped = h->hCtr->shadowSkipped;
         h->stats.levels = std::max<uint32_t>(h->stats.levels, (uint32_t)depth + 1);
         levelRanges.push_back({ h->interiorCount, h->hCtr->interiors });
         h->interiorCount = h->hCtr->interiors;
@@ -348,13 +360,16 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
     CK(cudaMemsetAsync(h->slots.p, 0, framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
     CK(cudaMemsetAsync(h->dCtr, 0, sizeof(rtk::Counters), st));
 
-    const long long n0 = (long long)p1rows.size() * (w - 1);
-    if (n0 > 0) {
+    const long long nPixels = (long long)p1rows.size() * (w - 1);
+    if (nPixels > 0) {
+        const long long n0 = rtk::raygenPaddedCount(w, (int)p1rows.size());   // whole 8x4 tiles, padding lanes idle
         reserveLevel(h, st, 0, n0);
         KernelSpan ks(h, st, RTB_K_RAYGEN);
         rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)p1rows.size(), h->rays[0].view());
         ks.done();
-        runLevels(h, st, n0, h->stats.primaryRays);
+        uint64_t padded = 0;
+        runLevels(h, st, n0, padded);
+        h->stats.primaryRays += (uint64_t)nPixels;
     }
     CK(cudaEventRecord(h->ev[1], st));
 
@@ -587,7 +602,7 @@ int rtb_trace(RtbHandle* h, const float* rays, int nRays, float* tuv, int32_t* o
         if (h->createFlags & (RTB_CREATE_EXACT_WALK | RTB_CREATE_COUNTERS))
             rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dCtr);
         else
-            rtk::k_trace<rtk::MODE_FAST><<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dCtr);
+            rtk::k_walk<false><<<persistentGrid(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, rtk::SurfQueue{}, nullptr, h->dCtr, &h->dCtr->walkCursor[0]);
         launchCheck();
         std::vector<float4> t4(nRays);
         std::vector<int> ob(nRays);

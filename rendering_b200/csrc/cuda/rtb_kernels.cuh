@@ -39,8 +39,11 @@ struct Counters {
     int slots;           // colour slots handed out
     int ssaaPixels;      // pixels flagged by k_sobel
     int overflow;        // set when a queue would overflow its capacity
+    unsigned int shadowSkipped;   // shadow rays not traced because their result cannot affect the pixel
+    int pad0;
     unsigned long long boxTests, triTests;            // closest-hit rays (k_trace)
     unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (k_shadow)
+    unsigned long long walkCursor[2];                  // k_walk work cursors: [0] closest-hit rays, [1] shadow rays
 };
 
 // Structure-of-arrays ray queue (one level).
@@ -99,18 +102,33 @@ __device__ __forceinline__ int warpAlloc(int* counter, bool want, int n)
 // ray generation
 // ------------------------------------------------------------------------------------------------
 // rows[] lists the image rows to render (each < height-1); every row has width-1 pixels because the
-// reference never renders the last column / row (getTiles, scene.cpp:369-372).
+// reference never renders the last column / row (getTiles, scene.cpp:369-372).  Queue order is 8x4
+// pixel tiles (one warp = one tile) so neighbouring lanes traverse the same BVH nodes; lanes that
+// fall outside the image are padding and carry dest = -1 (skipped by every later stage).
+__host__ __device__ inline long long raygenPaddedCount(int width, int nRows)
+{
+    const long long tilesX = (width - 1 + 7) / 8, tilesY = (nRows + 3) / 4;
+    return tilesX * tilesY * 32;
+}
 __global__ void k_raygen(Scene sc, const int* __restrict__ rows, int nRows, RayQueue q)
 {
     const int wm1 = sc.width - 1;
-    const long long total = (long long)nRows * wm1;
+    const int tilesX = (wm1 + 7) / 8;
+    const long long total = raygenPaddedCount(sc.width, nRows);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / wm1), x = (int)(i % wm1);
-        const int y = rows[r];
-        const V3 d = cameraDir(sc, (float)x + 0.5f, (float)y + 0.5f);
-        q.o[i] = make_float4(sc.camPos.x, sc.camPos.y, sc.camPos.z, 0.0f);
-        q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
-        q.dest[i] = y * sc.width + x;
+        const long long tile = i >> 5;
+        const int lane = (int)(i & 31);
+        const int x = (int)(tile % tilesX) * 8 + (lane & 7);
+        const int r = (int)(tile / tilesX) * 4 + (lane >> 3);
+        if (x < wm1 && r < nRows) {
+            const int y = rows[r];
+            const V3 d = cameraDir(sc, (float)x + 0.5f, (float)y + 0.5f);
+            q.o[i] = make_float4(sc.camPos.x, sc.camPos.y, sc.camPos.z, 0.0f);
+            q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+            q.dest[i] = y * sc.width + x;
+        } else {
+            q.dest[i] = -1;
+        }
     }
 }
 
@@ -184,6 +202,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int n, H
     int* stack = stackMem + threadIdx.x;
     unsigned long long nBox = 0, nTri = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (q.dest[i] < 0) { hits.obj[i] = -1; continue; }   // padding lane of a ray-generation tile
         const float4 o4 = q.o[i], d4 = q.d[i];
         const RayCtx r = makeRay(mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z));
         float tNear = FLT_MAX, uN = -1.0f, vN = -1.0f;
@@ -220,7 +239,7 @@ __global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int n,
         bool wantSurface = false;
         Surface s;
         int obj = -1;
-        if (i < n) {
+        if (i < n && q.dest[i] >= 0) {
             obj = hits.obj[i];
             const float4 d4 = q.d[i];
             const V3 d = mk(d4.x, d4.y, d4.z);
@@ -243,7 +262,7 @@ __global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int n,
 }
 
 // light sample k of a surface: direction FROM the light (normalised for point / area) and distance
-__device__ __forceinline__ void shadowSample(const Scene& sc, int k, V3 P, V3& L, float& dist)
+__device__ __forceinline__ bool shadowSample(const Scene& sc, int k, V3 P, V3& L, float& dist)
 {
     for (int i = 0; i < sc.nLights; ++i) {
         const Light& li = sc.lights[i];
@@ -258,28 +277,47 @@ __device__ __forceinline__ void shadowSample(const Scene& sc, int k, V3 P, V3& L
                 V3 I;
                 illuminate(li, P, L, I, dist);
             }
-            return;
+            return li.type == LIGHT_AREA;
         }
         k -= cnt;
     }
+    return false;
 }
 
 // Shadow trace (scene.cpp:787 etc.): Transparent objects cast no shadow (:733); an occluder counts
 // only when it is closer than the light (`tNear < intrInfo.tNear`, tNear preloaded by illuminate).
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, SurfQueue surf, unsigned char* __restrict__ vis, Counters* ctr)
+__global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQueue surf, unsigned char* __restrict__ vis, Counters* ctr)
 {
     __shared__ int stackMem[kStackDepth * kBlock];
     int* stack = stackMem + threadIdx.x;
     unsigned long long nBox = 0, nTri = 0;
+    unsigned int nSkipped = 0;
     const int S = sc.shadowRaysPerHit;
-    const long long total = (long long)ctr->surfaces * S;
+    const int nSurf = ctr->surfaces;
+    const long long total = (long long)nSurf * S;
     for (long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x; qi < total; qi += (long long)gridDim.x * blockDim.x) {
-        const int si = (int)(qi / S), k = (int)(qi % S);
+        // light-major order: a warp works on ONE light sample for 32 neighbouring surfaces
+        const int k = (int)(qi / nSurf), si = (int)(qi % nSurf);
         const float4 p4 = surf.pS[si], n4 = surf.nO[si];
         const V3 P = mk(p4.x, p4.y, p4.z), N = mk(n4.x, n4.y, n4.z);
         V3 L; float dist;
-        shadowSample(sc, k, P, L, dist);
+        const bool areaSample = shadowSample(sc, k, P, L, dist);
+        if (MODE != MODE_COUNT) {
+            // Dead-ray elision.  The visibility bit only ever multiplies max(0, N.-L) (Diffuse / Phong,
+            // scene.cpp:788,820) and pow(max(0, R.-D), nSpecular) (every material but Diffuse, :824,:867,
+            // :917); when those factors are exactly zero the reference's trace() cannot change the pixel,
+            // so the ray is not traced.  Bit-identical image; counted in Counters::shadowSkipped.
+            const int mat = sc.objects[__float_as_int(n4.w)].material;
+            bool needed = false;
+            if (mat == MAT_DIFFUSE || mat == MAT_PHONG) needed = maxf_(0.f, dot(N, -L)) > 0.f;
+            if (!needed && mat != MAT_DIFFUSE) {
+                const float4 d4 = q.d[__float_as_int(surf.cR[si].w)];
+                const float base = maxf_(0.f, dot(reflect(L, N), -mk(d4.x, d4.y, d4.z)));
+                needed = base > 0.f || (!areaSample && !(sc.objects[__float_as_int(n4.w)].nSpecular > 0.f));
+            }
+            if (!needed) { vis[(size_t)si * S + k] = 0; nSkipped++; continue; }
+        }
         const RayCtx r = makeRay(P + N * sc.bias, -L);
         float tNear = dist;
         bool blocked = false;
@@ -302,12 +340,189 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, SurfQueue surf, uns
             else ok = hitPlane(r, ob.pos, ob.normal, t);
             if (ok && t < tNear) { tNear = t; blocked = true; if (MODE != MODE_COUNT) break; }
         }
-        vis[qi] = blocked ? 0 : 1;
+        vis[(size_t)si * S + k] = blocked ? 0 : 1;
     }
+    if (nSkipped) atomicAdd(&ctr->shadowSkipped, nSkipped);
     if (MODE == MODE_COUNT) {
         atomicAdd(&ctr->boxTestsShadow, nBox);
         atomicAdd(&ctr->triTestsShadow, nTri);
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// persistent-threads traversal (fast path)
+// ------------------------------------------------------------------------------------------------
+// One kernel serves both ray kinds: ANY = false is Render::trace for primary / secondary rays
+// (closest hit over all objects), ANY = true is the shadow trace (any occluder closer than the
+// light, Transparent objects skipped).  The grid is sized to the machine, not to the queue: every
+// warp pulls rays from a global cursor, and whenever fewer than kRefillBelow lanes of a warp still
+// hold a live ray the finished lanes are refilled (ballot + one atomicAdd per warp), so a few long
+// rays never leave the other lanes idle.  Traversal is while-while over the search BVH with the
+// per-thread stack in shared memory.
+constexpr int kDone = (int)0x80000000;   // cursor value: no mesh traversal in progress
+constexpr int kRefillBelow = 22;
+
+template <bool ANY>
+__global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int nRays, HitQueue hits, SurfQueue surf,
+    unsigned char* __restrict__ vis, Counters* ctr, unsigned long long* cursor)
+{
+    __shared__ int stackMem[kStackDepth * kBlock];
+    int* stack = stackMem + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const bool cull = sc.flags & FLAG_CULL;
+    const int S = sc.shadowRaysPerHit;
+    const int nSurfRaw = ANY ? ctr->surfaces : 0;
+    const int nSurf = nSurfRaw > 0 ? nSurfRaw : 1;
+    const long long total = ANY ? (long long)nSurfRaw * S : (long long)nRays;
+
+    bool have = false, exhausted = false;
+    long long out = 0;                 // where the result goes: ray index (closest) or visibility index (ANY)
+    RayCtx r = makeRay(mk(0.f, 0.f, 0.f), mk(0.f, 0.f, -1.f));
+    float tNear = FLT_MAX, uN = -1.f, vN = -1.f;   // best over all objects / light distance
+    int objN = -1, triN = -1;
+    int obj = 0;                       // object loop position
+    int cur = kDone, sp = 0;           // search-BVH cursor of the mesh being walked
+    const Mesh* me = nullptr;
+    bool found = false;
+    int slotBest = 0x7fffffff, triM = -1;
+    float tM = FLT_MAX, uM = 0.f, vM = 0.f;
+    unsigned nSkipped = 0;
+
+    for (;;) {
+        // ---- refill idle lanes from the global cursor ----
+        if (!exhausted) {
+            const unsigned idle = __ballot_sync(FULL, !have);
+            if (idle) {
+                const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(cursor, (unsigned long long)nIdle);
+                base = __shfl_sync(FULL, base, leader);
+                if ((long long)base + nIdle >= total) exhausted = true;
+                const long long my = (long long)base + __popc(idle & ((1u << lane) - 1));
+                if (!have && my < total) {
+                    if (!ANY) {
+                        if (q.dest[my] < 0) {
+                            hits.obj[my] = -1;      // padding lane of a ray-generation tile
+                        } else {
+                            const float4 o4 = q.o[my], d4 = q.d[my];
+                            r = makeRay(mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z));
+                            tNear = FLT_MAX; uN = -1.f; vN = -1.f; objN = -1; triN = -1;
+                            out = my; obj = 0; cur = kDone; have = true;
+                        }
+                    } else {
+                        // light-major order: neighbouring lanes = neighbouring surfaces, same light sample
+                        const int k = (int)(my / nSurf), si = (int)(my % nSurf);
+                        const float4 p4 = surf.pS[si], n4 = surf.nO[si];
+                        const V3 P = mk(p4.x, p4.y, p4.z), N = mk(n4.x, n4.y, n4.z);
+                        V3 L; float dist;
+                        const bool areaSample = shadowSample(sc, k, P, L, dist);
+                        // dead-ray elision (see k_shadow): the bit cannot influence the pixel
+                        const Object& ob = sc.objects[__float_as_int(n4.w)];
+                        const int mat = ob.material;
+                        bool needed = false;
+                        if (mat == MAT_DIFFUSE || mat == MAT_PHONG) needed = maxf_(0.f, dot(N, -L)) > 0.f;
+                        if (!needed && mat != MAT_DIFFUSE) {
+                            const float4 d4 = q.d[__float_as_int(surf.cR[si].w)];
+                            const float base2 = maxf_(0.f, dot(reflect(L, N), -mk(d4.x, d4.y, d4.z)));
+                            needed = base2 > 0.f || (!areaSample && !(ob.nSpecular > 0.f));
+                        }
+                        out = (long long)si * S + k;
+                        if (!needed) { vis[out] = 0; nSkipped++; }
+                        else {
+                            r = makeRay(P + N * sc.bias, -L);
+                            tNear = dist; obj = 0; cur = kDone; have = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, have) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- traverse until the warp runs low on live rays ----
+        for (;;) {
+            if (have) {
+                if (cur == kDone) {
+                    // object loop of Render::trace (scene.cpp:731-754)
+                    if (obj >= sc.nObjects) {
+                        if (ANY) vis[out] = 1;
+                        else { hits.tuv[out] = make_float4(tNear, uN, vN, __int_as_float(triN)); hits.obj[out] = objN; }
+                        have = false;
+                    } else {
+                        const Object& ob = sc.objects[obj];
+                        if (ANY && ob.material == MAT_TRANSPARENT) {
+                            obj++;
+                        } else if (ob.type == OBJ_MESH) {
+                            me = &sc.meshes[ob.mesh];
+                            if (me->nNodes == 0) obj++;
+                            else { cur = 0; sp = 0; found = false; slotBest = 0x7fffffff; tM = tNear; }
+                        } else {
+                            float t = FLT_MAX;
+                            const bool ok = (ob.type == OBJ_SPHERE) ? hitSphere(r, ob.pos, ob.r2, t) : hitPlane(r, ob.pos, ob.normal, t);
+                            if (ok && t < tNear) {
+                                if (ANY) { vis[out] = 0; have = false; }
+                                else { tNear = t; uN = 0.f; vN = 0.f; objN = obj; triN = -1; }
+                            }
+                            obj++;
+                        }
+                    }
+                } else {
+                    // inner nodes
+                    while (cur >= 0) {
+                        const float4* nd = me->bvhNodes + (size_t)cur * 4;
+                        const float4 a = __ldg(nd), b = __ldg(nd + 1), c = __ldg(nd + 2), d = __ldg(nd + 3);
+                        const float tFar = ANY ? tNear : tM;
+                        bool h0, h1;
+                        const float e0 = slabEntry(r, a.x, a.y, a.z, a.w, b.x, b.y, tFar, h0);
+                        const float e1 = slabEntry(r, b.z, b.w, c.x, c.y, c.z, c.w, tFar, h1);
+                        const int c0 = __float_as_int(d.x), c1 = __float_as_int(d.y);
+                        if (h0 && h1) {
+                            const bool swap = e1 < e0;
+                            stack[sp * kBlock] = swap ? c0 : c1;
+                            sp++;
+                            cur = swap ? c1 : c0;
+                        } else if (h0) cur = c0;
+                        else if (h1) cur = c1;
+                        else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
+                        else { cur = kDone; break; }
+                    }
+                    // one leaf
+                    if (cur != kDone) {
+                        const int code = ~cur;
+                        const int first = code >> 3, count = (code & 7) + 1;
+                        const float4* tp = me->bvhTris + (size_t)first * 3;
+                        bool blocked = false;
+                        for (int k = 0; k < count; ++k, tp += 3) {
+                            const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                            float t, u, v;
+                            if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
+                            const int tri = __float_as_int(p0.w);
+                            if (ANY) {
+                                if (t < tNear && eligibleSlot(sc, *me, r, tri) >= 0) { blocked = true; break; }
+                            } else if (t < tM || (found && t == tM)) {
+                                const int slot = eligibleSlot(sc, *me, r, tri);
+                                if (slot >= 0 && (t < tM || slot < slotBest)) { tM = t; uM = u; vM = v; triM = tri; slotBest = slot; found = true; }
+                            }
+                        }
+                        if (ANY && blocked) { vis[out] = 0; have = false; cur = kDone; }
+                        else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
+                        else cur = kDone;
+                    }
+                    // mesh finished: fold into the running best (`tNear < intrInfo.tNear`, scene.cpp:740)
+                    if (have && cur == kDone) {
+                        if (!ANY && found) { tNear = tM; uN = uM; vN = vM; objN = obj; triN = triM; }
+                        obj++;
+                    }
+                }
+            }
+            const unsigned act = __ballot_sync(FULL, have);
+            if (act == 0 || (!exhausted && __popc(act) < kRefillBelow)) break;
+        }
+    }
+    if (ANY && nSkipped) atomicAdd(&ctr->shadowSkipped, nSkipped);
 }
 
 // ------------------------------------------------------------------------------------------------
