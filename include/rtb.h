@@ -175,6 +175,8 @@ void rtb_scene_free(RtbHostScene* hs);
 int  rtb_scene_tree_stats(const RtbHostScene* hs, int mesh, int64_t out[6]);
 /* saveImage contract (util.cpp:15-76) with the well-defined quantisation (uint8)(clamp(v)*255).    */
 int  rtb_save_bmp(const char* path, const float* fb, int width, int height);
+/* Writes header + the pixel bytes produced by rtb_render_bgr8 for the full frame.                   */
+int  rtb_save_bmp_bgr8(const char* path, const uint8_t* bgr, int width, int height);
 const char* rtb_host_last_error(void);
 
 /* ===================== device side: librtb_cuda.so ===================== */
@@ -194,6 +196,12 @@ int  rtb_create(const RtbScene* scene, int device, uint32_t createFlags, RtbHand
  * the handle's own stream).  For multi-GPU strips use rtb_render_strips.                           */
 int  rtb_render(RtbHandle* h, int y0, int y1, float* fb, float* pass1, int fbOnDevice,
                 void* stream, RtbStats* stats);
+
+/* Same frame, delivered as the pixel bytes saveImage writes after the 54-byte BMP header (util.cpp:46-56):
+ * rows bottom-up (image row y1-1 first), B,G,R per pixel, channel = (uint8)(clamp(0,1,v)*255), each row padded
+ * to a multiple of 4 bytes — (y1-y0) * ((3*width+3)&~3) bytes.  The conversion runs on the device, so a host
+ * buffer (onDevice == 0) receives a quarter of the bytes rtb_render copies back.                            */
+int  rtb_render_bgr8(RtbHandle* h, int y0, int y1, uint8_t* bgr, int onDevice, void* stream, RtbStats* stats);
 
 /* Render the rows owned by `rank` under a cyclic strip partition: strip s (stripRows rows) belongs
  * to rank s % worldSize.  Output is compact: owned rows in ascending order; returns their count in

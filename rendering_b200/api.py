@@ -91,6 +91,15 @@ def save_bmp(path: str, fb: np.ndarray) -> None:
         raise RtbError(rc, lib.rtb_host_last_error().decode())
 
 
+def save_bmp_bgr8(path: str, bgr: np.ndarray, width: int, height: int) -> None:
+    """Write the BMP from the pixel bytes Renderer.render_bgr8 returns (full frame)."""
+    bgr = np.ascontiguousarray(bgr, dtype=np.uint8)
+    lib = _ffi.host_lib()
+    rc = lib.rtb_save_bmp_bgr8(os.fsencode(path), bgr.ctypes.data, width, height)
+    if rc != _ffi.RTB_OK:
+        raise RtbError(rc, lib.rtb_host_last_error().decode())
+
+
 class Renderer:
     """Device-side renderer handle (librtb_cuda.so).  Raises if the CUDA library or a GPU is missing."""
 
@@ -119,6 +128,17 @@ class Renderer:
         st = _ffi.RtbStats()
         self._check(self._lib.rtb_render(self._h, y0, y1, fb.ctypes.data, p1.ctypes.data if want_pass1 else None, 0, None, C.byref(st)))
         return (fb, p1, st.as_dict()) if want_pass1 else (fb, st.as_dict())
+
+    def render_bgr8(self, y0: int = 0, y1: int | None = None, out: np.ndarray | None = None):
+        """The frame as saveImage's pixel bytes (src/util.cpp:46-56): uint8 (rows, row_bytes), bottom-up, B,G,R,
+        rows padded to 4 bytes; converted on the device."""
+        y1 = self.height if y1 is None else y1
+        shape = (y1 - y0, (self.width * 3 + 3) & ~3)
+        buf = out if out is not None else np.empty(shape, np.uint8)
+        assert buf.shape == shape and buf.dtype == np.uint8 and buf.flags.c_contiguous
+        st = _ffi.RtbStats()
+        self._check(self._lib.rtb_render_bgr8(self._h, y0, y1, buf.ctypes.data, 0, None, C.byref(st)))
+        return buf, st.as_dict()
 
     # -- device-buffer path: result stays in HBM (dev_ptr is a raw device pointer, e.g. tensor.data_ptr()) --
     def render_device(self, dev_ptr: int, y0: int = 0, y1: int | None = None, stream: int | None = None) -> dict:

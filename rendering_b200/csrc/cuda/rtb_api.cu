@@ -82,12 +82,26 @@ struct RtbHandle {
     rt::Scene scene{};                 // header with DEVICE pointers
     std::vector<void*> allocations;    // scene-lifetime device allocations
     std::vector<TextureRes> textures;
+    int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
+    int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
+    int walkBlocksPerSm[2] = { 1, 1 }; // resident CTAs per SM of k_walk<false> / k_walk<true> with that stack
 
     QueueBufs rays[2];
     DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, userRays, outStage;
-    rtk::Counters* dCtr = nullptr;
-    rtk::Counters* hCtr = nullptr;     // pinned
+    DevBuf ctrBuf;                     // FrameCtr followed by 2 passes x (levels + 1) LevelCtr
+    void* hCtr = nullptr;              // pinned mirror of ctrBuf
+    size_t ctrBytes = 0;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+
+    // capacities (in items) the buffers above currently provide; grown on demand, never shrunk
+    long long capLevel0 = 0;           // rays of a level-0 queue (ray generation)
+    long long capDeep = 0;             // rays of a deeper level's queue
+    long long capInterior = 0;         // interior records of one frame
+    long long capFlagged = 0;          // SSAA pixels
+    long long capSlots = 0;
+    // SSAA capacity hint carried from frame to frame: flagged pixels seen last time
+    long long flaggedSeen = 0;
+    std::vector<int> rowsAHost, rowsBHost;   // row lists currently resident in rowsA / rowsB
 
     // per-kernel timing: (kind, start, stop) spans recorded on the render stream, resolved at the end of a call
     struct Span { int kind; cudaEvent_t a, b; };
@@ -95,10 +109,18 @@ struct RtbHandle {
     std::vector<cudaEvent_t> eventPool;
     size_t eventsUsed = 0;
 
-    // per-call bookkeeping
-    int slotCount = 0;
-    int interiorCount = 0;
     RtbStats stats{};
+
+    rtk::FrameCtr* dFrame() const { return ctrBuf.as<rtk::FrameCtr>(); }
+    rtk::LevelCtr* dLevel(int pass, int level) const
+    {
+        return reinterpret_cast<rtk::LevelCtr*>(ctrBuf.as<char>() + sizeof(rtk::FrameCtr)) + (size_t)pass * (levels + 1) + level;
+    }
+    const rtk::FrameCtr* hFrame() const { return static_cast<const rtk::FrameCtr*>(hCtr); }
+    const rtk::LevelCtr* hLevel(int pass, int level) const
+    {
+        return reinterpret_cast<const rtk::LevelCtr*>(static_cast<const char*>(hCtr) + sizeof(rtk::FrameCtr)) + (size_t)pass * (levels + 1) + level;
+    }
 };
 
 namespace {
@@ -142,7 +164,7 @@ rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
 
 // Fast-path data of one mesh: search BVH over its unique triangles (bvh_build.h) and the tables that
 // let the kernel evaluate the reference tree's eligibility rule for a single triangle.
-void buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
+int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
 {
     rtpack::FastPath fp;
     rtpack::packFastPath(m, fp);
@@ -152,8 +174,12 @@ void buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
     d.triRefOff = upload(h, fp.triRefOff.data(), fp.triRefOff.size());
     d.triRefs = upload(h, fp.triRefs.data(), fp.triRefs.size());
     d.parent = upload(h, fp.parent.data(), fp.parent.size());
+    return fp.maxDepth;
 }
 
+size_t stackBytes(const RtbHandle* h) { return (size_t)h->stackEntries * rtk::kBlock * sizeof(int); }
+
+// grid-stride kernels: enough CTAs to fill the machine, never more than the work needs
 int gridFor(const RtbHandle* h, long long n, int block = rtk::kBlock, int perSm = 16)
 {
     const long long blocks = (n + block - 1) / block;
@@ -161,12 +187,12 @@ int gridFor(const RtbHandle* h, long long n, int block = rtk::kBlock, int perSm 
     return (int)std::max(1LL, std::min(blocks, cap));
 }
 
-// persistent kernels: one resident wave (6 CTAs of 128 threads per SM with the 32 KiB stack), never more
-// CTAs than there is work for
-int persistentGrid(const RtbHandle* h, long long n)
+// persistent kernels: exactly one resident wave (occupancy queried at create time), never more CTAs than
+// the queue's capacity could feed
+int persistentGrid(const RtbHandle* h, bool any, long long cap)
 {
-    const long long blocks = (n + rtk::kBlock - 1) / rtk::kBlock;
-    return (int)std::max(1LL, std::min(blocks, (long long)h->smCount * 6));
+    const long long blocks = (cap + rtk::kBlock - 1) / rtk::kBlock;
+    return (int)std::max(1LL, std::min(blocks, (long long)h->smCount * h->walkBlocksPerSm[any ? 1 : 0]));
 }
 
 void launchCheck() { CK(cudaGetLastError()); }
@@ -209,106 +235,85 @@ void resolveSpans(RtbHandle* h)
     h->eventsUsed = 0;
 }
 
-// Makes room for a level of n rays: hit / surface / visibility records for n rays, up to 2n rays in
-// the other queue, up to n more interior records and 2n more colour slots.
-void reserveLevel(RtbHandle* h, cudaStream_t st, int cur, long long n)
+// Sizes every per-frame buffer for: level-0 queues of up to n0 rays, deeper levels of up to nDeep rays,
+// nInterior interior records, nFlagged SSAA pixels on top of `framePixels` framebuffer slots.
+// Slot layout: [0, framePixels) framebuffer | [framePixels, +4*capFlagged) SSAA samples | 2 per interior record.
+void ensureCapacity(RtbHandle* h, cudaStream_t st, long long framePixels, long long n0, long long nDeep, long long nInterior, long long nFlagged)
 {
+    if (std::max(n0, nDeep) > (1LL << 28)) throw CudaError{ cudaErrorMemoryAllocation, "ray queue larger than 2^28 rays" };
+    h->capLevel0 = std::max(h->capLevel0, n0);
+    h->capDeep = std::max(h->capDeep, h->levels > 1 ? nDeep : 0LL);
+    h->capInterior = std::max(h->capInterior, h->levels > 1 ? nInterior : 0LL);
+    h->capFlagged = std::max(h->capFlagged, nFlagged);
     const long long S = std::max(1, h->scene.shadowRaysPerHit);
-    if (n > (1LL << 28)) throw CudaError{ cudaErrorMemoryAllocation, "ray queue larger than 2^28 rays" };
-    h->rays[cur].reserve((size_t)n, st, true);
-    h->rays[cur ^ 1].reserve((size_t)(2 * n), st, false);
-    h->hitTuv.reserve((size_t)n * sizeof(float4), st, false);
-    h->hitObj.reserve((size_t)n * sizeof(int), st, false);
-    h->surfP.reserve((size_t)n * sizeof(float4), st, false);
-    h->surfN.reserve((size_t)n * sizeof(float4), st, false);
-    h->surfC.reserve((size_t)n * sizeof(float4), st, false);
-    h->vis.reserve((size_t)(n * S), st, false);
-    h->interiors.reserve((size_t)(h->interiorCount + n) * sizeof(rtk::Interior), st, true);
-    h->slots.reserve((size_t)(h->slotCount + 2 * n) * 3 * sizeof(float), st, true);
+    const long long nMax = std::max(h->capLevel0, h->capDeep);
+    // level d lives in rays[d & 1]: queue 0 holds level 0 and the even deeper levels, queue 1 the odd ones
+    h->rays[0].reserve((size_t)std::max(1LL, nMax), st, false);
+    h->rays[1].reserve((size_t)std::max(1LL, h->capDeep), st, false);
+    h->hitTuv.reserve((size_t)nMax * sizeof(float4), st, false);
+    h->hitObj.reserve((size_t)nMax * sizeof(int), st, false);
+    h->surfP.reserve((size_t)nMax * sizeof(float4), st, false);
+    h->surfN.reserve((size_t)nMax * sizeof(float4), st, false);
+    h->surfC.reserve((size_t)nMax * sizeof(float4), st, false);
+    h->vis.reserve((size_t)(nMax * S), st, false);
+    h->interiors.reserve((size_t)std::max(1LL, h->capInterior) * sizeof(rtk::Interior), st, false);
+    h->flagged.reserve((size_t)std::max(1LL, h->capFlagged) * sizeof(int), st, false);
+    h->capSlots = framePixels + 4 * h->capFlagged + 2 * h->capInterior;
+    h->slots.reserve((size_t)h->capSlots * 3 * sizeof(float), st, false);
 }
 
-// Runs castRay for the n0 rays sitting in queue 0, level by level, then folds the interior records.
-void runLevels(RtbHandle* h, cudaStream_t st, long long n0, uint64_t& tracedFirstLevel)
+// Enqueues castRay for the rays sitting in queue 0 of `pass`, level by level, then folds the interior
+// records deepest level first.  Nothing here waits for the device: every kernel reads its work size
+// from the LevelCtr its predecessor filled.
+void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixels)
 {
     const bool count = h->createFlags & RTB_CREATE_COUNTERS;
     const bool exact = h->createFlags & RTB_CREATE_EXACT_WALK;
     const rt::Scene& sc = h->scene;
-    std::vector<std::pair<int, int>> levelRanges;
-    int cur = 0;
-    long long n = n0;
-    tracedFirstLevel += (uint64_t)n0;
-    const int interiorStart = h->interiorCount;
-    (void)interiorStart;
-    for (int depth = 0; depth <= sc.maxRayDepth && n > 0; ++depth) {
-        reserveLevel(h, st, cur, n);
-        if (depth > 0) h->stats.secondaryRays += (uint64_t)n;
-        // reset the per-level counters, keep the running ones
-        h->hCtr->nextRays = 0;
-        h->hCtr->surfaces = 0;
-        h->hCtr->interiors = h->interiorCount;
-        h->hCtr->slots = h->slotCount;
-        CK(cudaMemcpyAsync(h->dCtr, h->hCtr, offsetof(rtk::Counters, ssaaPixels), cudaMemcpyHostToDevice, st));
-        h->stats.h2dBytes += offsetof(rtk::Counters, ssaaPixels);
-
-        const rtk::RayQueue q = h->rays[cur].view(), next = h->rays[cur ^ 1].view();
-        const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
-        const rtk::SurfQueue surf{ h->surfP.as<float4>(), h->surfN.as<float4>(), h->surfC.as<float4>() };
-        const int nextCap = (int)std::min<size_t>(h->rays[cur ^ 1].dest.bytes / sizeof(int), 1u << 30);
-        const int interiorCap = (int)std::min<size_t>(h->interiors.bytes / sizeof(rtk::Interior), 1u << 30);
-        const int slotCap = (int)std::min<size_t>(h->slots.bytes / (3 * sizeof(float)), 1u << 30);
-
+    const size_t smem = stackBytes(h);
+    const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
+    const rtk::SurfQueue surf{ h->surfP.as<float4>(), h->surfN.as<float4>(), h->surfC.as<float4>() };
+    unsigned char* vis = h->vis.as<unsigned char>();
+    const int slotBase = (int)(framePixels + 4 * h->capFlagged);
+    for (int depth = 0; depth < h->levels; ++depth) {
+        const long long cap = depth == 0 ? h->capLevel0 : h->capDeep;
+        const long long capNext = h->capDeep;
+        const rtk::RayQueue q = h->rays[depth & 1].view(), next = h->rays[(depth + 1) & 1].view();
+        rtk::LevelCtr* lv = h->dLevel(pass, depth);
         {
             KernelSpan ks(h, st, RTB_K_TRACE);
-            if (count) rtk::k_trace<rtk::MODE_COUNT><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
-            else if (exact) rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, h->dCtr);
-            else {
-                CK(cudaMemsetAsync(&h->dCtr->walkCursor[0], 0, 2 * sizeof(unsigned long long), st));
-                rtk::k_walk<false><<<persistentGrid(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, surf, h->vis.as<unsigned char>(), h->dCtr, &h->dCtr->walkCursor[0]);
-            }
+            if (count) rtk::k_trace<rtk::MODE_COUNT><<<gridFor(h, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, h->dFrame(), lv);
+            else if (exact) rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, h->dFrame(), lv);
+            else rtk::k_walk<false><<<persistentGrid(h, false, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv);
             ks.done();
         }
         {
             KernelSpan ks(h, st, RTB_K_SURFACE);
-            rtk::k_surface<<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, (int)n, hits, surf, h->slots.as<float>(), h->dCtr);
+            rtk::k_surface<<<gridFor(h, cap), rtk::kBlock, 0, st>>>(sc, q, (int)cap, hits, surf, h->slots.as<float>(), lv);
             ks.done();
         }
         if (!(sc.flags & rt::FLAG_SHOW_NORMALS)) {
             if (sc.shadowRaysPerHit > 0) {
-                const long long maxShadow = n * sc.shadowRaysPerHit;
+                const long long maxShadow = cap * sc.shadowRaysPerHit;
                 KernelSpan ks(h, st, RTB_K_SHADOW);
-                if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, q, surf, h->vis.as<unsigned char>(), h->dCtr);
-                else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, 0, st>>>(sc, q, surf, h->vis.as<unsigned char>(), h->dCtr);
-                else rtk::k_walk<true><<<persistentGrid(h, maxShadow), rtk::kBlock, 0, st>>>(sc, q, 0, hits, surf, h->vis.as<unsigned char>(), h->dCtr, &h->dCtr->walkCursor[1]);
+                if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, smem, st>>>(sc, q, surf, vis, h->dFrame(), lv);
+                else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, smem, st>>>(sc, q, surf, vis, h->dFrame(), lv);
+                else rtk::k_walk<true><<<persistentGrid(h, true, maxShadow), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv);
                 ks.done();
             }
             KernelSpan ks(h, st, RTB_K_SHADE);
-            rtk::k_shade<<<gridFor(h, n), rtk::kBlock, 0, st>>>(sc, q, surf, h->vis.as<unsigned char>(), depth, next, nextCap,
-                h->interiors.as<rtk::Interior>(), interiorCap, h->slots.as<float>(), slotCap, h->dCtr);
-            ks.done();
-        }
-        CK(cudaMemcpyAsync(h->hCtr, h->dCtr, sizeof(rtk::Counters), cudaMemcpyDeviceToHost, st));
-        h->stats.d2hBytes += sizeof(rtk::Counters);
-        CK(cudaStreamSynchronize(st));
-        if (h->hCtr->overflow) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queue overflow" };
-        h->stats.shadowRays += (uint64_t)h->hCtr->surfaces * (uint64_t)sc.shadowRaysPerHit;
-        h->stats.shadowRaysSkipped = h->hCtr->shadowSkipped;
-        h->stats.levels = std::max<uint32_t>(h->stats.levels, (uint32_t)depth + 1);
-        levelRanges.push_back({ h->interiorCount, h->hCtr->interiors });
-        h->interiorCount = h->hCtr->interiors;
-        h->slotCount = h->hCtr->slots;
-        n = h->hCtr->nextRays;
-        cur ^= 1;
-    }
-    for (int l = (int)levelRanges.size() - 1; l >= 0; --l) {
-        const int first = levelRanges[l].first, last = levelRanges[l].second;
-        if (last > first) {
-            KernelSpan ks(h, st, RTB_K_COMBINE);
-            rtk::k_combine<<<gridFor(h, last - first), rtk::kBlock, 0, st>>>(h->interiors.as<rtk::Interior>(), first, last, h->slots.as<float>());
+            rtk::k_shade<<<gridFor(h, cap), rtk::kBlock, 0, st>>>(sc, q, surf, vis, depth, next, (int)capNext,
+                h->interiors.as<rtk::Interior>(), (int)h->capInterior, h->slots.as<float>(), slotBase, (int)h->capSlots, h->dFrame(), lv);
             ks.done();
         }
     }
-    // the queue holding level 0 must be queue 0 again for the next caller
-    if (h->rays[0].o.p == nullptr) h->rays[0].reserve(1, st, false);
+    for (int l = h->levels - 2; l >= 0; --l) {   // the deepest level never has children
+        KernelSpan ks(h, st, RTB_K_COMBINE);
+        // the LevelCtr entries of both passes are one flat array: records of earlier passes / shallower levels come first
+        rtk::k_combine<<<gridFor(h, h->capInterior), rtk::kBlock, 0, st>>>(h->interiors.as<rtk::Interior>(), h->dLevel(0, 0),
+            pass * (h->levels + 1) + l, (int)h->capInterior, h->slots.as<float>());
+        ks.done();
+    }
 }
 
 void beginCall(RtbHandle* h)
@@ -317,9 +322,6 @@ void beginCall(RtbHandle* h)
     h->stats = RtbStats{};
     h->spans.clear();
     h->eventsUsed = 0;
-    h->slotCount = 0;
-    h->interiorCount = 0;
-    std::memset(h->hCtr, 0, sizeof(rtk::Counters));
 }
 
 float elapsed(cudaEvent_t a, cudaEvent_t b)
@@ -329,113 +331,176 @@ float elapsed(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+// Reads the frame's counters back (the one synchronisation of a frame) and folds them into the stats.
+// Returns the overflow bits.
+int finishFrame(RtbHandle* h, cudaStream_t st, int passes)
+{
+    CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
+    h->stats.d2hBytes += h->ctrBytes;
+    CK(cudaStreamSynchronize(st));
+    const rtk::FrameCtr* fc = h->hFrame();
+    const uint64_t S = (uint64_t)h->scene.shadowRaysPerHit;
+    for (int p = 0; p < passes; ++p)
+        for (int l = 0; l < h->levels; ++l) {
+            const rtk::LevelCtr* lv = h->hLevel(p, l);
+            if (l > 0) h->stats.secondaryRays += (uint64_t)lv->nRays;
+            if (!(h->scene.flags & rt::FLAG_SHOW_NORMALS)) h->stats.shadowRays += (uint64_t)lv->nSurf * S;
+            if (lv->nRays > 0) h->stats.levels = std::max<uint32_t>(h->stats.levels, (uint32_t)l + 1);
+        }
+    h->stats.shadowRaysSkipped = fc->shadowSkipped;
+    h->stats.ssaaPixels = (uint64_t)fc->ssaaPixels;
+    if (h->createFlags & RTB_CREATE_COUNTERS) {
+        h->stats.boxTestsShadow = fc->boxTestsShadow;
+        h->stats.triTestsShadow = fc->triTestsShadow;
+        h->stats.boxTests = fc->boxTests + fc->boxTestsShadow;
+        h->stats.triTests = fc->triTests + fc->triTestsShadow;
+    }
+    return fc->overflow;
+}
+
+// After an overflow: grow what ran out (the counters say how much was wanted) so the re-run fits.
+void growAfterOverflow(RtbHandle* h, int bits, int passes)
+{
+    if (bits & rtk::OVF_FLAGGED) h->capFlagged = std::max(2 * h->capFlagged, (long long)h->hFrame()->ssaaPixels);
+    if (bits & rtk::OVF_RAYS) {
+        long long want = 2 * h->capDeep;
+        for (int p = 0; p < passes; ++p)
+            for (int l = 1; l <= h->levels; ++l) want = std::max(want, (long long)h->hLevel(p, l)->nRays);
+        h->capDeep = want;
+    }
+    if (bits & rtk::OVF_INTERIORS) h->capInterior = std::max(2 * h->capInterior, (long long)h->hFrame()->interiors);
+}
+
+enum OutputKind { OUT_FLOAT = 0, OUT_BGR8 = 1 };
+
+void uploadRows(RtbHandle* h, cudaStream_t st, DevBuf& buf, std::vector<int>& resident, const std::vector<int>& rows)
+{
+    if (rows == resident && buf.p) return;
+    buf.reserve(std::max<size_t>(1, rows.size()) * sizeof(int), st, false);
+    // the copy is stream-ordered, but `rows` may die before it runs: keep the source alive in `resident`
+    CK(cudaStreamSynchronize(st));
+    resident = rows;
+    CK(cudaMemcpyAsync(buf.p, resident.data(), resident.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    h->stats.h2dBytes += resident.size() * sizeof(int);
+}
+
 // Renders the rows in `owned` (ascending) into `out` (compact, owned rows in order).
-int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pass1, int fbOnDevice, void* stream, RtbStats* statsOut)
+int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pass1, int fbOnDevice, void* stream, RtbStats* statsOut,
+    OutputKind kind = OUT_FLOAT)
 {
     cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
     beginCall(h);
     const rt::Scene& sc = h->scene;
     const int w = sc.width, ht = sc.height;
-    const size_t framePixels = (size_t)w * ht;
+    const long long framePixels = (long long)w * ht;
+    const bool ssaa = (sc.flags & rt::FLAG_SSAA) && !owned.empty();
 
     // pass-1 rows: owned rows plus a one-row halo for the Sobel window, minus the never-rendered last row
     std::vector<int> p1rows;
     {
         std::vector<char> need(ht, 0);
-        const bool ssaa = sc.flags & rt::FLAG_SSAA;
         for (int y : owned)
             for (int dy = ssaa ? -1 : 0; dy <= (ssaa ? 1 : 0); ++dy)
                 if (y + dy >= 0 && y + dy < ht - 1) need[y + dy] = 1;
         for (int y = 0; y < ht; ++y) if (need[y]) p1rows.push_back(y);
     }
-    h->rowsA.reserve(std::max<size_t>(1, p1rows.size()) * sizeof(int), st, false);
-    h->rowsB.reserve(std::max<size_t>(1, owned.size()) * sizeof(int), st, false);
-    CK(cudaMemcpyAsync(h->rowsA.p, p1rows.data(), p1rows.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->rowsB.p, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    h->stats.h2dBytes += (p1rows.size() + owned.size()) * sizeof(int);
-
-    CK(cudaEventRecord(h->ev[0], st));
-    h->slotCount = (int)framePixels;
-    h->slots.reserve(framePixels * 3 * sizeof(float), st, false);
-    CK(cudaMemsetAsync(h->slots.p, 0, framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
-    CK(cudaMemsetAsync(h->dCtr, 0, sizeof(rtk::Counters), st));
+    uploadRows(h, st, h->rowsA, h->rowsAHost, p1rows);
+    uploadRows(h, st, h->rowsB, h->rowsBHost, owned);
 
     const long long nPixels = (long long)p1rows.size() * (w - 1);
-    if (nPixels > 0) {
-        const long long n0 = rtk::raygenPaddedCount(w, (int)p1rows.size());   // whole 8x4 tiles, padding lanes idle
-        reserveLevel(h, st, 0, n0);
-        KernelSpan ks(h, st, RTB_K_RAYGEN);
-        rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)p1rows.size(), h->rays[0].view());
-        ks.done();
-        uint64_t padded = 0;
-        runLevels(h, st, n0, padded);
-        h->stats.primaryRays += (uint64_t)nPixels;
-    }
-    CK(cudaEventRecord(h->ev[1], st));
+    const long long n0 = nPixels > 0 ? rtk::raygenPaddedCount(w, (int)p1rows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
+    const long long interiorPixels = ssaa ? (long long)owned.size() * w : 0;
+    // SSAA capacity: what the last frame flagged plus head-room, at least 1/16 of the owned pixels; a frame that
+    // flags more sets OVF_FLAGGED and is re-run with the exact count
+    long long flaggedCap = ssaa ? std::min(interiorPixels, std::max(interiorPixels / 16, h->flaggedSeen + h->flaggedSeen / 4 + 1024)) : 0;
+    const size_t outRowBytes = kind == OUT_BGR8 ? (size_t)((w * 3 + 3) & ~3) : (size_t)w * 3 * sizeof(float);
+    const size_t outBytes = owned.size() * outRowBytes;
+    const bool contiguous = !owned.empty() && owned.back() - owned.front() + 1 == (int)owned.size();
 
-    const size_t outFloats = owned.size() * (size_t)w * 3;
-    auto emit = [&](float* dst) {
-        if (!dst || owned.empty()) return;
-        float* target = dst;
-        if (!fbOnDevice) {
-            h->outStage.reserve(outFloats * sizeof(float), st, false);
-            target = h->outStage.as<float>();
-        }
-        KernelSpan ks(h, st, RTB_K_OUTPUT);
-        rtk::k_gather_rows<<<gridFor(h, (long long)outFloats), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(), (int)owned.size(), target);
-        ks.done();
-        if (!fbOnDevice) {
-            CK(cudaMemcpyAsync(dst, target, outFloats * sizeof(float), cudaMemcpyDeviceToHost, st));
-            h->stats.d2hBytes += outFloats * sizeof(float);
-        }
-    };
-    if (pass1) { emit(pass1); if (!fbOnDevice) CK(cudaStreamSynchronize(st)); }
+    for (int attempt = 0;; ++attempt) {
+        const long long level0 = std::max(n0, 4 * std::max(flaggedCap, h->capFlagged));
+        ensureCapacity(h, st, framePixels, level0, 2 * level0, 2 * level0, flaggedCap);
+        const int sampleBase = (int)framePixels;
 
-    int nFlagged = 0;
-    if ((sc.flags & rt::FLAG_SSAA) && !owned.empty()) {
-        h->flagged.reserve(owned.size() * (size_t)w * sizeof(int), st, false);
-        {
-            KernelSpan ks(h, st, RTB_K_SOBEL);
-            rtk::k_sobel<<<gridFor(h, (long long)owned.size() * w), rtk::kBlock, 0, st>>>(w, ht, h->slots.as<float>(), h->rowsB.as<int>(),
-                (int)owned.size(), h->flagged.as<int>(), h->dCtr);
-            ks.done();
-        }
-        CK(cudaMemcpyAsync(h->hCtr, h->dCtr, sizeof(rtk::Counters), cudaMemcpyDeviceToHost, st));
-        h->stats.d2hBytes += sizeof(rtk::Counters);
-        CK(cudaEventRecord(h->ev[2], st));
-        CK(cudaStreamSynchronize(st));
-        nFlagged = h->hCtr->ssaaPixels;
-        h->stats.ssaaPixels = (uint64_t)nFlagged;
-        if (nFlagged > 0) {
-            const long long n1 = 4LL * nFlagged;
-            const int slotBase = h->slotCount;
-            h->slotCount += (int)n1;
-            reserveLevel(h, st, 0, n1);
+        CK(cudaEventRecord(h->ev[0], st));
+        CK(cudaMemsetAsync(h->slots.p, 0, (size_t)framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
+        CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
+        if (n0 > 0) {
             {
                 KernelSpan ks(h, st, RTB_K_RAYGEN);
-                rtk::k_ssaa_gen<<<gridFor(h, n1), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), nFlagged, slotBase, h->rays[0].view());
+                rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)p1rows.size(), h->rays[0].view(), h->dLevel(0, 0));
                 ks.done();
             }
-            runLevels(h, st, n1, h->stats.primaryRays);
-            KernelSpan ks(h, st, RTB_K_OUTPUT);
-            rtk::k_ssaa_resolve<<<gridFor(h, nFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), nFlagged, slotBase, h->slots.as<float>());
-            ks.done();
+            enqueueLevels(h, st, 0, framePixels);
         }
-    } else {
-        CK(cudaEventRecord(h->ev[2], st));
-    }
-    emit(fb);
-    CK(cudaEventRecord(h->ev[3], st));
-    CK(cudaStreamSynchronize(st));
+        CK(cudaEventRecord(h->ev[1], st));
 
-    if (h->createFlags & RTB_CREATE_COUNTERS) {
-        CK(cudaMemcpy(h->hCtr, h->dCtr, sizeof(rtk::Counters), cudaMemcpyDeviceToHost));
-        h->stats.boxTestsShadow = h->hCtr->boxTestsShadow;
-        h->stats.triTestsShadow = h->hCtr->triTestsShadow;
-        h->stats.boxTests = h->hCtr->boxTests + h->hCtr->boxTestsShadow;
-        h->stats.triTests = h->hCtr->triTests + h->hCtr->triTestsShadow;
+        auto emit = [&](void* dst, OutputKind k, size_t bytes) {
+            if (!dst || owned.empty()) return;
+            const bool direct = k == OUT_FLOAT && contiguous;   // the rows already lie contiguously in the slot array
+            void* target = dst;
+            if (!fbOnDevice && !direct) {
+                h->outStage.reserve(bytes, st, false);
+                target = h->outStage.p;
+            }
+            if (direct) {
+                const float* src = h->slots.as<float>() + (size_t)owned.front() * w * 3;
+                CK(cudaMemcpyAsync(dst, src, bytes, fbOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            } else {
+                KernelSpan ks(h, st, RTB_K_OUTPUT);
+                if (k == OUT_BGR8)
+                    rtk::k_quantize_bgr8<<<gridFor(h, (long long)(bytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                        (int)owned.size(), static_cast<unsigned int*>(target));
+                else
+                    rtk::k_gather_rows<<<gridFor(h, (long long)(bytes / 16)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                        (int)owned.size(), static_cast<float*>(target));
+                ks.done();
+                if (!fbOnDevice) CK(cudaMemcpyAsync(dst, target, bytes, cudaMemcpyDeviceToHost, st));
+            }
+            if (!fbOnDevice) h->stats.d2hBytes += bytes;
+        };
+        if (pass1) emit(pass1, OUT_FLOAT, owned.size() * (size_t)w * 3 * sizeof(float));
+
+        if (ssaa) {
+            {
+                KernelSpan ks(h, st, RTB_K_SOBEL);
+                rtk::k_sobel<<<gridFor(h, interiorPixels), rtk::kBlock, 0, st>>>(w, ht, h->slots.as<float>(), h->rowsB.as<int>(),
+                    (int)owned.size(), h->flagged.as<int>(), (int)h->capFlagged, h->dFrame());
+                ks.done();
+            }
+            CK(cudaEventRecord(h->ev[2], st));
+            {
+                KernelSpan ks(h, st, RTB_K_RAYGEN);
+                rtk::k_ssaa_gen<<<gridFor(h, 4 * h->capFlagged), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
+                    h->rays[0].view(), h->dFrame(), h->dLevel(1, 0));
+                ks.done();
+            }
+            enqueueLevels(h, st, 1, framePixels);
+            KernelSpan ks(h, st, RTB_K_OUTPUT);
+            rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
+                h->slots.as<float>(), h->dFrame());
+            ks.done();
+        } else {
+            CK(cudaEventRecord(h->ev[2], st));
+        }
+        emit(fb, kind, outBytes);
+        CK(cudaEventRecord(h->ev[3], st));
+
+        const int overflow = finishFrame(h, st, ssaa ? 2 : 1);
+        if (!overflow) break;
+        if (attempt >= 8 + h->levels) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queues still overflow after repeated growth" };
+        // discard this attempt's statistics and run the frame again with larger queues
+        growAfterOverflow(h, overflow, ssaa ? 2 : 1);
+        flaggedCap = std::max(flaggedCap, h->capFlagged);
+        const uint64_t h2d = h->stats.h2dBytes;
+        resolveSpans(h);
+        h->stats = RtbStats{};
+        h->stats.h2dBytes = h2d;
     }
+
     resolveSpans(h);
+    h->flaggedSeen = (long long)h->stats.ssaaPixels;
+    h->stats.primaryRays = (uint64_t)nPixels + 4 * h->stats.ssaaPixels;
     h->stats.rays = h->stats.primaryRays + h->stats.secondaryRays + h->stats.shadowRays;
     h->stats.msPass1 = elapsed(h->ev[0], h->ev[1]);
     h->stats.msSobel = elapsed(h->ev[1], h->ev[2]);
@@ -443,6 +508,38 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, float* fb, float* pa
     h->stats.msTotal = elapsed(h->ev[0], h->ev[3]);
     if (statsOut) *statsOut = h->stats;
     return RTB_OK;
+}
+
+// castRay / trace on caller-supplied rays: one pass, level-0 queue = the rays themselves
+void enqueueUserRays(RtbHandle* h, cudaStream_t st, const float* rays, int nRays, bool shade)
+{
+    beginCall(h);
+    for (int attempt = 0;; ++attempt) {
+        ensureCapacity(h, st, nRays, nRays, 2LL * nRays, 2LL * nRays, 0);
+        h->userRays.reserve((size_t)nRays * 6 * sizeof(float), st, false);
+        CK(cudaMemcpyAsync(h->userRays.p, rays, (size_t)nRays * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
+        rtk::k_rays_from_user<<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->userRays.as<float>(), nRays, 0, h->rays[0].view(), h->dLevel(0, 0));
+        launchCheck();
+        if (shade) {
+            enqueueLevels(h, st, 0, nRays);
+        } else {
+            const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
+            if (h->createFlags & (RTB_CREATE_EXACT_WALK | RTB_CREATE_COUNTERS))
+                rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, nRays), rtk::kBlock, stackBytes(h), st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dFrame(), h->dLevel(0, 0));
+            else
+                rtk::k_walk<false><<<persistentGrid(h, false, nRays), rtk::kBlock, stackBytes(h), st>>>(h->scene, h->rays[0].view(), nRays, hits,
+                    rtk::SurfQueue{}, nullptr, h->dFrame(), h->dLevel(0, 0));
+            launchCheck();
+        }
+        const int overflow = finishFrame(h, st, 1);
+        if (!overflow) break;
+        if (attempt >= 8 + h->levels) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queues still overflow after repeated growth" };
+        growAfterOverflow(h, overflow, 1);
+        resolveSpans(h);
+        h->stats = RtbStats{};
+    }
+    resolveSpans(h);
 }
 
 template <typename F>
@@ -481,7 +578,7 @@ void destroyHandle(RtbHandle* h)
     for (DevBuf* b : { &h->hitTuv, &h->hitObj, &h->surfP, &h->surfN, &h->surfC, &h->vis, &h->interiors, &h->slots, &h->flagged,
              &h->rowsA, &h->rowsB, &h->userRays, &h->outStage })
         b->release();
-    if (h->dCtr) cudaFree(h->dCtr);
+    h->ctrBuf.release();
     if (h->hCtr) cudaFreeHost(h->hCtr);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->eventPool) cudaEventDestroy(e);
@@ -516,8 +613,6 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         h->smCount = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
         for (cudaEvent_t& e : h->ev) CK(cudaEventCreate(&e));
-        CK(cudaMalloc((void**)&h->dCtr, sizeof(rtk::Counters)));
-        CK(cudaMallocHost((void**)&h->hCtr, sizeof(rtk::Counters)));
 
         rtpack::packHeader(*s, h->scene);
         std::vector<rt::Object> objects;
@@ -540,9 +635,24 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             d.normal = uploadImage(h, m.normalMap);
             d.specular = uploadImage(h, m.specularMap);
             d.nNodes = m.nNodes; d.nSlots = m.nRefs; d.nTris = m.nTris; d.maxDepth = pm.maxDepth;
-            if (m.nNodes > 0) buildFastPath(h, m, d);
+            if (createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK)) h->stackEntries = std::max(h->stackEntries, pm.maxDepth + 1);
+            if (m.nNodes > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
             meshes.push_back(d);
         }
+        // recursion levels: only Reflective / Transparent hits spawn children (scene.cpp:854-941)
+        bool spawns = false;
+        for (int i = 0; i < s->nObjects; ++i)
+            spawns |= s->objects[i].material == RTB_MAT_REFLECTIVE || s->objects[i].material == RTB_MAT_TRANSPARENT;
+        h->levels = spawns ? std::max(0, s->maxRayDepth) + 1 : 1;
+        h->ctrBytes = sizeof(rtk::FrameCtr) + 2 * (size_t)(h->levels + 1) * sizeof(rtk::LevelCtr);
+        h->ctrBuf.reserve(h->ctrBytes, h->ownStream, false);
+        CK(cudaMallocHost(&h->hCtr, h->ctrBytes));
+        std::memset(h->hCtr, 0, h->ctrBytes);
+        // one resident wave of the persistent traversal kernels with this scene's stack size
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[0], rtk::k_walk<false>, rtk::kBlock, stackBytes(h)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[1], rtk::k_walk<true>, rtk::kBlock, stackBytes(h)));
+        h->walkBlocksPerSm[0] = std::max(1, h->walkBlocksPerSm[0]);
+        h->walkBlocksPerSm[1] = std::max(1, h->walkBlocksPerSm[1]);
         h->scene.objects = upload(h, objects.data(), objects.size());
         h->scene.lights = upload(h, lights.data(), lights.size());
         h->scene.meshes = upload(h, meshes.data(), meshes.size());
@@ -564,6 +674,17 @@ int rtb_render(RtbHandle* h, int y0, int y1, float* fb, float* pass1, int fbOnDe
         std::vector<int> rows;
         for (int y = y0; y < y1; ++y) rows.push_back(y);
         return renderRows(h, rows, fb, pass1, fbOnDevice, stream, stats);
+    });
+}
+
+int rtb_render_bgr8(RtbHandle* h, int y0, int y1, uint8_t* bgr, int onDevice, void* stream, RtbStats* stats)
+{
+    if (!h || !bgr) { g_err = "null argument"; return RTB_ERR_ARG; }
+    if (y0 < 0 || y1 > h->scene.height || y0 > y1) { g_err = "row range outside the image"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        std::vector<int> rows;
+        for (int y = y0; y < y1; ++y) rows.push_back(y);
+        return renderRows(h, rows, bgr, nullptr, onDevice, stream, stats, OUT_BGR8);
     });
 }
 
@@ -591,23 +712,11 @@ int rtb_trace(RtbHandle* h, const float* rays, int nRays, float* tuv, int32_t* o
     if (nRays == 0) return RTB_OK;
     return guarded([&]() {
         cudaStream_t st = h->ownStream;
-        beginCall(h);
-        reserveLevel(h, st, 0, nRays);
-        h->userRays.reserve((size_t)nRays * 6 * sizeof(float), st, false);
-        CK(cudaMemcpyAsync(h->userRays.p, rays, (size_t)nRays * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(h->dCtr, 0, sizeof(rtk::Counters), st));
-        rtk::k_rays_from_user<<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->userRays.as<float>(), nRays, 0, h->rays[0].view());
-        launchCheck();
-        const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
-        if (h->createFlags & (RTB_CREATE_EXACT_WALK | RTB_CREATE_COUNTERS))
-            rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dCtr);
-        else
-            rtk::k_walk<false><<<persistentGrid(h, nRays), rtk::kBlock, 0, st>>>(h->scene, h->rays[0].view(), nRays, hits, rtk::SurfQueue{}, nullptr, h->dCtr, &h->dCtr->walkCursor[0]);
-        launchCheck();
+        enqueueUserRays(h, st, rays, nRays, false);
         std::vector<float4> t4(nRays);
         std::vector<int> ob(nRays);
-        CK(cudaMemcpyAsync(t4.data(), hits.tuv, (size_t)nRays * sizeof(float4), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ob.data(), hits.obj, (size_t)nRays * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(t4.data(), h->hitTuv.p, (size_t)nRays * sizeof(float4), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ob.data(), h->hitObj.p, (size_t)nRays * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         for (int i = 0; i < nRays; ++i) {
             tuv[3 * i] = t4[i].x; tuv[3 * i + 1] = t4[i].y; tuv[3 * i + 2] = t4[i].z;
@@ -626,15 +735,7 @@ int rtb_cast(RtbHandle* h, const float* rays, int nRays, float* rgb)
     if (nRays == 0) return RTB_OK;
     return guarded([&]() {
         cudaStream_t st = h->ownStream;
-        beginCall(h);
-        h->slotCount = nRays;
-        reserveLevel(h, st, 0, nRays);
-        h->userRays.reserve((size_t)nRays * 6 * sizeof(float), st, false);
-        CK(cudaMemcpyAsync(h->userRays.p, rays, (size_t)nRays * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(h->dCtr, 0, sizeof(rtk::Counters), st));
-        rtk::k_rays_from_user<<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->userRays.as<float>(), nRays, 0, h->rays[0].view());
-        launchCheck();
-        runLevels(h, st, nRays, h->stats.primaryRays);
+        enqueueUserRays(h, st, rays, nRays, true);
         CK(cudaMemcpyAsync(rgb, h->slots.p, (size_t)nRays * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         return RTB_OK;

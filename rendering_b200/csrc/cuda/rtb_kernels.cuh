@@ -31,19 +31,28 @@ using namespace rt;
 constexpr int kBlock = 128;          // threads per CTA for the ray kernels
 constexpr int kStackDepth = 64;      // per-thread traversal stack entries (shared memory)
 
-// Device-side bump counters.  Reset / read back by the host once per level.
-struct Counters {
-    int nextRays;        // rays appended to the next level's queue
-    int surfaces;        // compacted hits of this level
-    int interiors;       // Reflective / Transparent records (persist until k_combine)
-    int slots;           // colour slots handed out
+// Device-side counters.  The host zeroes both structures once at the start of a frame and reads them
+// back once at its end: nothing in between needs the host, so a whole frame (both passes, every
+// recursion level) is enqueued without a single synchronisation.
+struct FrameCtr {
+    int interiors;       // Reflective / Transparent records handed out (persist until k_combine)
+    int slots;           // child colour slots handed out (offset by the frame's slot base)
     int ssaaPixels;      // pixels flagged by k_sobel
-    int overflow;        // set when a queue would overflow its capacity
+    int overflow;        // OVF_* bits: a queue would have overflowed its capacity -> the host grows it and re-runs
     unsigned int shadowSkipped;   // shadow rays not traced because their result cannot affect the pixel
     int pad0;
-    unsigned long long boxTests, triTests;            // closest-hit rays (k_trace)
-    unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (k_shadow)
-    unsigned long long walkCursor[2];                  // k_walk work cursors: [0] closest-hit rays, [1] shadow rays
+    unsigned long long boxTests, triTests;             // closest-hit rays (counting build)
+    unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (counting build)
+};
+enum { OVF_RAYS = 1, OVF_INTERIORS = 2, OVF_FLAGGED = 4 };
+
+// One per (pass, recursion level).
+struct LevelCtr {
+    int nRays;           // rays in this level's queue (written by ray generation / the previous level's k_shade)
+    int nSurf;           // compacted hits of this level (k_surface)
+    int interiorEnd;     // one past the last interior record of this level (atomicMax by k_shade)
+    int pad0;
+    unsigned long long cursor[2];   // k_walk work cursors: [0] closest-hit rays, [1] shadow rays
 };
 
 // Structure-of-arrays ray queue (one level).
@@ -110,11 +119,12 @@ __host__ __device__ inline long long raygenPaddedCount(int width, int nRows)
     const long long tilesX = (width - 1 + 7) / 8, tilesY = (nRows + 3) / 4;
     return tilesX * tilesY * 32;
 }
-__global__ void k_raygen(Scene sc, const int* __restrict__ rows, int nRows, RayQueue q)
+__global__ void k_raygen(Scene sc, const int* __restrict__ rows, int nRows, RayQueue q, LevelCtr* lv)
 {
     const int wm1 = sc.width - 1;
     const int tilesX = (wm1 + 7) / 8;
     const long long total = raygenPaddedCount(sc.width, nRows);
+    if (blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long tile = i >> 5;
         const int lane = (int)(i & 31);
@@ -133,8 +143,9 @@ __global__ void k_raygen(Scene sc, const int* __restrict__ rows, int nRows, RayQ
 }
 
 // caller-supplied rays (rtb_trace / rtb_cast): 6 floats per ray
-__global__ void k_rays_from_user(const float* __restrict__ rays, int n, int destBase, RayQueue q)
+__global__ void k_rays_from_user(const float* __restrict__ rays, int n, int destBase, RayQueue q, LevelCtr* lv)
 {
+    if (blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         q.o[i] = make_float4(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2], 0.0f);
         q.d[i] = make_float4(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5], 0.0f);
@@ -196,11 +207,12 @@ enum { MODE_FAST = 0, MODE_EXACT = 1, MODE_COUNT = 2 };
 
 // Render::trace for primary / secondary rays (scene.cpp:724-756)
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int n, HitQueue hits, Counters* ctr)
+__global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int cap, HitQueue hits, FrameCtr* ctr, const LevelCtr* lv)
 {
-    __shared__ int stackMem[kStackDepth * kBlock];
+    extern __shared__ int stackMem[];
     int* stack = stackMem + threadIdx.x;
     unsigned long long nBox = 0, nTri = 0;
+    const int n = min(lv->nRays, cap);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (q.dest[i] < 0) { hits.obj[i] = -1; continue; }   // padding lane of a ray-generation tile
         const float4 o4 = q.o[i], d4 = q.d[i];
@@ -231,9 +243,10 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int n, H
 // ------------------------------------------------------------------------------------------------
 // surface stage: castRay between trace() and the light loops (scene.cpp:762-775, 945)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int n, HitQueue hits, SurfQueue surf,
-    float* __restrict__ slots, Counters* ctr)
+__global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
+    float* __restrict__ slots, LevelCtr* lv)
 {
+    const int n = min(lv->nRays, cap);
     const int nPadded = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPadded; i += gridDim.x * blockDim.x) {
         bool wantSurface = false;
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int n,
                 else wantSurface = true;
             }
         }
-        const int si = warpAlloc(&ctr->surfaces, wantSurface, 1);
+        const int si = warpAlloc(&lv->nSurf, wantSurface, 1);
         if (wantSurface) {
             surf.pS[si] = make_float4(s.P.x, s.P.y, s.P.z, s.specCoef);
             surf.nO[si] = make_float4(s.N.x, s.N.y, s.N.z, __int_as_float(obj));
@@ -287,14 +300,15 @@ __device__ __forceinline__ bool shadowSample(const Scene& sc, int k, V3 P, V3& L
 // Shadow trace (scene.cpp:787 etc.): Transparent objects cast no shadow (:733); an occluder counts
 // only when it is closer than the light (`tNear < intrInfo.tNear`, tNear preloaded by illuminate).
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQueue surf, unsigned char* __restrict__ vis, Counters* ctr)
+__global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQueue surf, unsigned char* __restrict__ vis, FrameCtr* ctr,
+    const LevelCtr* lv)
 {
-    __shared__ int stackMem[kStackDepth * kBlock];
+    extern __shared__ int stackMem[];
     int* stack = stackMem + threadIdx.x;
     unsigned long long nBox = 0, nTri = 0;
     unsigned int nSkipped = 0;
     const int S = sc.shadowRaysPerHit;
-    const int nSurf = ctr->surfaces;
+    const int nSurf = lv->nSurf;
     const long long total = (long long)nSurf * S;
     for (long long qi = blockIdx.x * (long long)blockDim.x + threadIdx.x; qi < total; qi += (long long)gridDim.x * blockDim.x) {
         // light-major order: a warp works on ONE light sample for 32 neighbouring surfaces
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQue
             // Dead-ray elision.  The visibility bit only ever multiplies max(0, N.-L) (Diffuse / Phong,
             // scene.cpp:788,820) and pow(max(0, R.-D), nSpecular) (every material but Diffuse, :824,:867,
             // :917); when those factors are exactly zero the reference's trace() cannot change the pixel,
-            // so the ray is not traced.  Bit-identical image; counted in Counters::shadowSkipped.
+            // so the ray is not traced.  Bit-identical image; counted in FrameCtr::shadowSkipped.
             const int mat = sc.objects[__float_as_int(n4.w)].material;
             bool needed = false;
             if (mat == MAT_DIFFUSE || mat == MAT_PHONG) needed = maxf_(0.f, dot(N, -L)) > 0.f;
@@ -364,16 +378,18 @@ constexpr int kDone = (int)0x80000000;   // cursor value: no mesh traversal in p
 constexpr int kRefillBelow = 22;
 
 template <bool ANY>
-__global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int nRays, HitQueue hits, SurfQueue surf,
-    unsigned char* __restrict__ vis, Counters* ctr, unsigned long long* cursor)
+__global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
+    unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv)
 {
-    __shared__ int stackMem[kStackDepth * kBlock];
+    extern __shared__ int stackMem[];
     int* stack = stackMem + threadIdx.x;
+    unsigned long long* cursor = &lv->cursor[ANY ? 1 : 0];
+    const int nRays = min(lv->nRays, cap);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const bool cull = sc.flags & FLAG_CULL;
     const int S = sc.shadowRaysPerHit;
-    const int nSurfRaw = ANY ? ctr->surfaces : 0;
+    const int nSurfRaw = ANY ? lv->nSurf : 0;
     const int nSurf = nSurfRaw > 0 ? nSurfRaw : 1;
     const long long total = ANY ? (long long)nSurfRaw * S : (long long)nRays;
 
@@ -530,10 +546,11 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int nRays
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_shade(Scene sc, RayQueue q, SurfQueue surf, const unsigned char* __restrict__ vis,
     int depth, RayQueue next, int nextCap, Interior* __restrict__ interiors, int interiorCap,
-    float* __restrict__ slots, int slotCap, Counters* ctr)
+    float* __restrict__ slots, int slotBase, int slotCap, FrameCtr* ctr, LevelCtr* lv)
 {
     const int S = sc.shadowRaysPerHit;
-    const int n = ctr->surfaces;
+    const int n = lv->nSurf;
+    LevelCtr* lvNext = lv + 1;
     const int nPadded = (n + 31) & ~31;
     for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < nPadded; si += gridDim.x * blockDim.x) {
         int nChildren = 0;
@@ -625,24 +642,34 @@ __global__ void __launch_bounds__(kBlock) k_shade(Scene sc, RayQueue q, SurfQueu
         }
         // bump-allocate: interior record, two colour slots, nChildren queue entries
         const int ii = warpAlloc(&ctr->interiors, wantInterior, 1);
-        const int cs = warpAlloc(&ctr->slots, wantInterior, 2);
-        const int q1 = warpAlloc(&ctr->nextRays, nChildren >= 1, 1);
-        const int q2 = warpAlloc(&ctr->nextRays, nChildren >= 2, 1);
+        const int cs = slotBase + warpAlloc(&ctr->slots, wantInterior, 2);
+        const int q1 = warpAlloc(&lvNext->nRays, nChildren >= 1, 1);
+        const int q2 = warpAlloc(&lvNext->nRays, nChildren >= 2, 1);
         if (wantInterior) {
-            if (ii >= interiorCap || cs + 2 > slotCap || (nChildren >= 1 && q1 >= nextCap) || (nChildren >= 2 && q2 >= nextCap)) {
-                ctr->overflow = 1;
+            const bool fits1 = q1 < nextCap, fits2 = nChildren < 2 || q2 < nextCap;
+            if (ii >= interiorCap || cs + 2 > slotCap) {
+                atomicOr(&ctr->overflow, OVF_INTERIORS);
+                // queue entries already claimed must not stay uninitialised: mark them as padding
+                if (fits1) next.dest[q1] = -1;
+                if (nChildren == 2 && fits2) next.dest[q2] = -1;
             } else {
+                if (!fits1 || !fits2) atomicOr(&ctr->overflow, OVF_RAYS);   // the host re-runs the frame with larger queues
                 rec.child = cs;
                 interiors[ii] = rec;
+                atomicMax(&lv->interiorEnd, ii + 1);
                 // kind 3 keeps its single (reflection) child in slot child+1 so k_combine reads one layout
                 const int firstSlot = (rec.kind == 3) ? cs + 1 : cs;
-                next.o[q1] = make_float4(childO[0].x, childO[0].y, childO[0].z, 0.0f);
-                next.d[q1] = make_float4(childD[0].x, childD[0].y, childD[0].z, 0.0f);
-                next.dest[q1] = firstSlot;
+                if (fits1) {
+                    next.o[q1] = make_float4(childO[0].x, childO[0].y, childO[0].z, 0.0f);
+                    next.d[q1] = make_float4(childD[0].x, childD[0].y, childD[0].z, 0.0f);
+                    next.dest[q1] = firstSlot;
+                } else storeSlot(slots, firstSlot, mk(0.0f, 0.0f, 0.0f));
                 if (nChildren == 2) {
-                    next.o[q2] = make_float4(childO[1].x, childO[1].y, childO[1].z, 0.0f);
-                    next.d[q2] = make_float4(childD[1].x, childD[1].y, childD[1].z, 0.0f);
-                    next.dest[q2] = cs + 1;
+                    if (fits2) {
+                        next.o[q2] = make_float4(childO[1].x, childO[1].y, childO[1].z, 0.0f);
+                        next.d[q2] = make_float4(childD[1].x, childD[1].y, childD[1].z, 0.0f);
+                        next.dest[q2] = cs + 1;
+                    } else storeSlot(slots, cs + 1, mk(0.0f, 0.0f, 0.0f));
                 }
             }
         }
@@ -650,8 +677,14 @@ __global__ void __launch_bounds__(kBlock) k_shade(Scene sc, RayQueue q, SurfQueu
 }
 
 // Fold children into parents for interior records [first, last): castRay's return path.
-__global__ void k_combine(const Interior* __restrict__ interiors, int first, int last, float* __restrict__ slots)
+// Level `level`'s records are [max(interiorEnd of the shallower levels), interiorEnd[level]): levels run one
+// after the other and records are bump-allocated, so each level owns one contiguous range.
+__global__ void k_combine(const Interior* __restrict__ interiors, const LevelCtr* __restrict__ lv, int level, int interiorCap,
+    float* __restrict__ slots)
 {
+    int first = 0;
+    for (int j = 0; j < level; ++j) first = max(first, lv[j].interiorEnd);
+    const int last = min(max(first, lv[level].interiorEnd), interiorCap);
     for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < last; i += gridDim.x * blockDim.x) {
         const Interior rec = interiors[i];
         const V3 spec = mk(rec.sx, rec.sy, rec.sz);
@@ -672,17 +705,23 @@ __global__ void k_combine(const Interior* __restrict__ interiors, int first, int
 // ------------------------------------------------------------------------------------------------
 // SSAA: Sobel mask on the unclamped float frame, then 4 re-traced samples per flagged pixel
 // ------------------------------------------------------------------------------------------------
-// rows[]: image rows owned by this call; only interior pixels get a flag (scene.cpp:554-555)
+// rows[]: image rows owned by this call; only interior pixels get a flag (scene.cpp:554-555).  Pixels are
+// visited in the 8x4 tiles of ray generation (one warp = one tile), so the compacted list keeps
+// neighbouring pixels — and with them the 4 samples of each — next to each other in the SSAA ray queue.
 __global__ void k_sobel(int width, int height, const float* __restrict__ fb, const int* __restrict__ rows, int nRows,
-    int* __restrict__ flagged, Counters* ctr)
+    int* __restrict__ flagged, int flaggedCap, FrameCtr* ctr)
 {
-    const long long total = (long long)nRows * width;
-    const long long padded = (total + 31) & ~31LL;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < padded; i += (long long)gridDim.x * blockDim.x) {
+    const int tilesX = (width + 7) / 8;
+    const long long total = (long long)tilesX * ((nRows + 3) / 4) * 32;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         bool flag = false;
         int pix = 0;
-        if (i < total) {
-            const int y = rows[i / width], x = (int)(i % width);
+        const long long tile = i >> 5;
+        const int lane = (int)(i & 31);
+        const int x = (int)(tile % tilesX) * 8 + (lane & 7);
+        const int r = (int)(tile / tilesX) * 4 + (lane >> 3);
+        if (x < width && r < nRows) {
+            const int y = rows[r];
             if (y >= 1 && y < height - 1 && x >= 1 && x < width - 1) {
                 V3 gx = mk(0.0f, 0.0f, 0.0f), gy = mk(0.0f, 0.0f, 0.0f);
                 const float op[3][3] = { { -1, 0, 1 }, { -2, 0, 2 }, { -1, 0, 1 } };
@@ -701,13 +740,18 @@ __global__ void k_sobel(int width, int height, const float* __restrict__ fb, con
             }
         }
         const int f = warpAlloc(&ctr->ssaaPixels, flag, 1);
-        if (flag) flagged[f] = pix;
+        if (flag) {
+            if (f < flaggedCap) flagged[f] = pix;
+            else atomicOr(&ctr->overflow, OVF_FLAGGED);
+        }
     }
 }
 
-__global__ void k_ssaa_gen(Scene sc, const int* __restrict__ flagged, int nFlagged, int slotBase, RayQueue q)
+__global__ void k_ssaa_gen(Scene sc, const int* __restrict__ flagged, int flaggedCap, int slotBase, RayQueue q, const FrameCtr* ctr,
+    LevelCtr* lv)
 {
-    const int total = nFlagged * 4;
+    const int total = min(ctr->ssaaPixels, flaggedCap) * 4;
+    if (blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = total;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int pix = flagged[i >> 2], k = i & 3;
         const int y = pix / sc.width, x = pix % sc.width;
@@ -720,8 +764,9 @@ __global__ void k_ssaa_gen(Scene sc, const int* __restrict__ flagged, int nFlagg
     }
 }
 
-__global__ void k_ssaa_resolve(const int* __restrict__ flagged, int nFlagged, int slotBase, float* __restrict__ slots)
+__global__ void k_ssaa_resolve(const int* __restrict__ flagged, int flaggedCap, int slotBase, float* __restrict__ slots, const FrameCtr* ctr)
 {
+    const int nFlagged = min(ctr->ssaaPixels, flaggedCap);
     for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nFlagged; f += gridDim.x * blockDim.x) {
         V3 c = mk(0.0f, 0.0f, 0.0f);
 #pragma unroll
@@ -730,14 +775,57 @@ __global__ void k_ssaa_resolve(const int* __restrict__ flagged, int nFlagged, in
     }
 }
 
-// copy owned rows of the full-frame slot region into a compact output
+// ------------------------------------------------------------------------------------------------
+// output
+// ------------------------------------------------------------------------------------------------
+// copy owned rows of the full-frame slot region into a compact output, 16 bytes per thread
+// (rowFloats = 3*width is a multiple of 4 whenever width is; the scalar tail covers the rest)
 __global__ void k_gather_rows(const float* __restrict__ fb, int width, const int* __restrict__ rows, int nRows, float* __restrict__ out)
 {
-    const long long rowFloats = (long long)width * 3;
+    const int rowFloats = width * 3;
+    if ((rowFloats & 3) == 0 && (((size_t)fb | (size_t)out) & 15) == 0) {
+        const int rowVecs = rowFloats >> 2;
+        const long long total = (long long)nRows * rowVecs;
+        const float4* src = reinterpret_cast<const float4*>(fb);
+        float4* dst = reinterpret_cast<float4*>(out);
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / rowVecs);
+            dst[i] = src[(long long)rows[r] * rowVecs + (i - (long long)r * rowVecs)];
+        }
+        return;
+    }
     const long long total = (long long)nRows * rowFloats;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / rowFloats);
         out[i] = fb[(long long)rows[r] * rowFloats + (i % rowFloats)];
+    }
+}
+
+// saveImage's pixel conversion on the device (util.cpp:46-56): rows bottom-up, B,G,R byte order, each channel
+// (uint8)(clamp(0,1,v)*255), rows padded to a multiple of 4 bytes.  Output row j holds image row rows[nRows-1-j].
+// One thread converts 4 bytes (= 4 channels) and stores them as one 32-bit word.
+__global__ void k_quantize_bgr8(const float* __restrict__ fb, int width, const int* __restrict__ rows, int nRows, unsigned int* __restrict__ out)
+{
+    const int rowBytes = (width * 3 + 3) & ~3;
+    const int rowWords = rowBytes >> 2;
+    const long long total = (long long)nRows * rowWords;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i / rowWords);
+        const int wordInRow = (int)(i - (long long)j * rowWords);
+        const float* src = fb + (long long)rows[nRows - 1 - j] * width * 3;
+        unsigned int word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int byteInRow = wordInRow * 4 + b;
+            unsigned int v = 0;
+            if (byteInRow < width * 3) {
+                const int px = byteInRow / 3, ch = 2 - (byteInRow - px * 3);   // B,G,R
+                const float c = clampf_(0.0f, 1.0f, src[px * 3 + ch]);
+                v = (unsigned int)(unsigned char)(c * 255);
+            }
+            word |= v << (8 * b);
+        }
+        out[i] = word;
     }
 }
 

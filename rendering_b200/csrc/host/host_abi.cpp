@@ -97,6 +97,12 @@ int rtb_save_bmp(const char* path, const float* fb, int width, int height)
     return guarded([&]() { rtb::saveBMP(path, fb, width, height); return RTB_OK; });
 }
 
+int rtb_save_bmp_bgr8(const char* path, const uint8_t* bgr, int width, int height)
+{
+    if (!path || !bgr || width <= 0 || height <= 0) { g_lastError = "bad argument"; return RTB_ERR_ARG; }
+    return guarded([&]() { rtb::saveBMPBytes(path, bgr, width, height); return RTB_OK; });
+}
+
 const char* rtb_host_last_error(void) { return g_lastError.c_str(); }
 
 } // extern "C"

@@ -22,7 +22,7 @@ namespace {
 
 struct Backend {
     decltype(&rtb_create) create = nullptr;
-    decltype(&rtb_render) render = nullptr;
+    decltype(&rtb_render_bgr8) renderBgr8 = nullptr;
     decltype(&rtb_destroy) destroy = nullptr;
     decltype(&rtb_last_error) lastError = nullptr;
 };
@@ -46,10 +46,10 @@ Backend loadBackend()
     if (!so) throw rtb::Error(RTB_ERR_CUDA, std::string("cannot load CUDA backend: ") + dlerror());
     Backend b;
     b.create = (decltype(b.create))dlsym(so, "rtb_create");
-    b.render = (decltype(b.render))dlsym(so, "rtb_render");
+    b.renderBgr8 = (decltype(b.renderBgr8))dlsym(so, "rtb_render_bgr8");
     b.destroy = (decltype(b.destroy))dlsym(so, "rtb_destroy");
     b.lastError = (decltype(b.lastError))dlsym(so, "rtb_last_error");
-    if (!b.create || !b.render || !b.destroy || !b.lastError)
+    if (!b.create || !b.renderBgr8 || !b.destroy || !b.lastError)
         throw rtb::Error(RTB_ERR_CUDA, "CUDA backend " + path + " lacks rtb_* symbols");
     return b;
 }
@@ -82,9 +82,11 @@ void Scene::render()
         if (backend.create(&flat.view, devEnv ? atoi(devEnv) : 0, RTB_CREATE_DEFAULT, &handle) != RTB_OK)
             throw rtb::Error(RTB_ERR_CUDA, backend.lastError());
 
-        std::vector<float> frameBuffer((size_t)options.width * options.height * 3, 0.0f);
+        // the frame comes back as the BMP's pixel bytes: clamp / quantise / BGR / row flip of saveImage
+        // (util.cpp:46-56) run on the device, a quarter of the float framebuffer's bytes cross PCIe
+        std::vector<unsigned char> pixelBytes((size_t)((options.width * 3 + 3) & ~(size_t)3) * options.height, 0);
         RtbStats stats{};
-        const int rc = backend.render(handle, 0, (int)options.height, frameBuffer.data(), nullptr, 0, nullptr, &stats);
+        const int rc = backend.renderBgr8(handle, 0, (int)options.height, pixelBytes.data(), 0, nullptr, &stats);
         const std::string err = rc == RTB_OK ? "" : backend.lastError();
         backend.destroy(handle);
         if (rc != RTB_OK) throw rtb::Error(rc, err);
@@ -94,7 +96,7 @@ void Scene::render()
         report("MSAA", stats.msSobel + stats.msSSAA);
         if (options::imageOutput) {
             const std::string path = options.imageName + ".bmp";
-            rtb::saveBMP(path, frameBuffer.data(), (int)options.width, (int)options.height);
+            rtb::saveBMPBytes(path, pixelBytes.data(), (int)options.width, (int)options.height);
             printf("Successfully wrote to output file %s\n", path.c_str());
         }
         if (options::collectStatistics) {

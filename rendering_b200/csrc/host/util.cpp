@@ -84,7 +84,8 @@ void loadBMP(const std::string& filename, std::vector<uint8_t>& rgb, int& width,
     for (size_t i = 0; i + 2 < rgb.size(); i += 3) std::swap(rgb[i], rgb[i + 2]);
 }
 
-void saveBMP(const std::string& path, const float* fb, int width, int height)
+namespace {
+void writeBMP(const std::string& path, const unsigned char* body, int width, int height)
 {
     const int pad = (4 - (width * 3) % 4) % 4;
     const uint32_t dataSize = (uint32_t)((width * 3 + pad) * height);
@@ -101,7 +102,18 @@ void saveBMP(const std::string& path, const float* fb, int width, int height)
     put32(34, dataSize);
     put32(38, 2835);
     put32(42, 2835);
-    std::vector<unsigned char> rows((size_t)dataSize, 0);
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) throw Error(RTB_ERR_IO, "Could not open output file " + path);
+    fwrite(header, 1, sizeof header, f);
+    fwrite(body, 1, dataSize, f);
+    fclose(f);
+}
+} // namespace
+
+void saveBMP(const std::string& path, const float* fb, int width, int height)
+{
+    const int pad = (4 - (width * 3) % 4) % 4;
+    std::vector<unsigned char> rows((size_t)(width * 3 + pad) * height, 0);
     size_t o = 0;
     for (int r = height - 1; r >= 0; --r) {
         const float* src = fb + (size_t)r * width * 3;
@@ -112,11 +124,9 @@ void saveBMP(const std::string& path, const float* fb, int width, int height)
             }
         o += pad;
     }
-    FILE* f = fopen(path.c_str(), "wb");
-    if (!f) throw Error(RTB_ERR_IO, "Could not open output file " + path);
-    fwrite(header, 1, sizeof header, f);
-    fwrite(rows.data(), 1, rows.size(), f);
-    fclose(f);
+    writeBMP(path, rows.data(), width, height);
 }
+
+void saveBMPBytes(const std::string& path, const unsigned char* bgr, int width, int height) { writeBMP(path, bgr, width, height); }
 
 } // namespace rtb

@@ -30,5 +30,7 @@ void loadBMP(const std::string& filename, std::vector<uint8_t>& rgb, int& width,
 
 // saveImage contract (util.cpp:15-76): bottom-up rows, BGR, byte = (uint8)(clamp(v,0,1)*255).
 void saveBMP(const std::string& path, const float* fb, int width, int height);
+// same file from already-converted pixel bytes (rtb_render_bgr8: bottom-up rows, BGR, padded to 4)
+void saveBMPBytes(const std::string& path, const unsigned char* bgr, int width, int height);
 
 } // namespace rtb

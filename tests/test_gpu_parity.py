@@ -155,6 +155,63 @@ def test_device_buffer_path_matches_host_buffer_path():
     assert st["kernelLaunches"] > 0 and sum(st["launchesKernel"]) == st["kernelLaunches"]
 
 
+def test_pixel_byte_output_equals_quantised_float_frame():
+    # rtb_render_bgr8 = saveImage's clamp / *255 truncation / BGR / bottom-up rows (util.cpp:46-56) on the device
+    for text in (MIXED_SCENE, MIXED_SCENE.replace("width=96", "width=99")):     # 99*3 bytes: rows padded by 3
+        sc = rb.Scene(text=text)
+        r = rb.Renderer(sc)
+        fb, _ = r.render()
+        px, st = r.render_bgr8()
+        w, h = sc.width, sc.height
+        want = np.zeros((h, (w * 3 + 3) & ~3), np.uint8)
+        want[:, : w * 3] = (np.clip(fb, 0, 1) * np.float32(255)).astype(np.uint8)[::-1, :, ::-1].reshape(h, w * 3)
+        assert np.array_equal(px, want)
+        assert st["d2hBytes"] < fb.nbytes / 3
+        part, _ = r.render_bgr8(10, 31)
+        assert np.array_equal(part, want[h - 31: h - 10])
+
+
+GLASS_HALL = """
+[options]
+width=64
+height=48
+max_ray_depth=6
+background_color=0.3,0.5,0.7
+[light]
+type=point
+position=0,3,0
+intensity=0.9
+[object]
+type=sphere
+pos=0,0,-2.2
+radius=2
+material=transparent,1.5
+[object]
+type=sphere
+pos=0,0,-2.2
+radius=0.7
+material=transparent,1.3
+[object]
+type=plane
+pos=0,-2.5,0
+normal=0,1,0
+material=reflective
+[end]
+"""
+
+
+def test_ray_tree_growth_beyond_the_initial_queues():
+    # nested glass: every hit spawns two children for several levels, so the deeper queues outgrow their first
+    # sizing; the frame is re-run with larger queues (FrameCtr::overflow) and must still equal the oracle
+    sc = rb.Scene(text=GLASS_HALL)
+    fb, p1, st = check_against_oracle(sc, exact=False, counters=False)
+    assert st["secondaryRays"] > 4 * st["primaryRays"] and st["levels"] == 7
+    r = rb.Renderer(sc)
+    a, _ = r.render()
+    b, _ = r.render()      # second frame runs in already-grown queues
+    assert np.array_equal(a.view(np.uint32), fb.view(np.uint32)) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_trace_and_cast_queries_vs_oracle():
     rng = np.random.default_rng(7)
     scenes = [rb.Scene(text=MIXED_SCENE)]

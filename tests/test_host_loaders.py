@@ -133,3 +133,18 @@ def test_bmp_roundtrip(tmp_path):
     assert (sky.width, sky.height) == (8, 5)
     got = np.ctypeslib.as_array(sky.rgb, (5, 8, 3))
     np.testing.assert_array_equal(got, want[::-1])
+
+
+def test_bmp_from_pixel_bytes_equals_bmp_from_floats(tmp_path):
+    # rtb_save_bmp_bgr8 takes the bytes rtb_render_bgr8 produces; built here with numpy the way the device does
+    from rendering_b200.api import save_bmp_bgr8
+    rng = np.random.default_rng(1)
+    for w, h in ((8, 5), (7, 3), (10, 4)):          # widths whose rows need 0 / 3 / 2 padding bytes
+        fb = rng.random((h, w, 3), dtype=np.float32) * 1.4 - 0.2
+        a, b = str(tmp_path / "a.bmp"), str(tmp_path / "b.bmp")
+        save_bmp(a, fb)
+        row_bytes = (w * 3 + 3) & ~3
+        body = np.zeros((h, row_bytes), np.uint8)
+        body[:, : w * 3] = (np.clip(fb, 0, 1) * np.float32(255)).astype(np.uint8)[::-1, :, ::-1].reshape(h, w * 3)
+        save_bmp_bgr8(b, body, w, h)
+        assert open(a, "rb").read() == open(b, "rb").read()
