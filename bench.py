@@ -10,11 +10,14 @@ exactly (tests/test_gpu_parity.py), so both arms share the numerator.
 
 ours:       value  = rays / device time, scene and queues resident in HBM, framebuffer left in HBM,
                      CUDA events on the render stream, L2 flushed between timed frames.
-            e2e    = the same frame through the public host-buffer call (rtb_render with a pinned
-                     HOST framebuffer: row lists / counters H2D, framebuffer D2H inside the call).
-            roofline = the traversal kernel (k_trace, Render::trace for primary/secondary rays),
-                     algorithmic bytes from the reference's own work counts:
-                     48 B/ray + 32 B/box test + 48 B/triangle test, over its CUDA-event time.
+            e2e    = the same frame through the public host-buffer call Scene::render() makes
+                     (rtb_render_bgr8 into pinned HOST memory: the frame arrives as the BMP's pixel
+                     bytes, D2H inside the call); e2e_float = rtb_render with a float32 host framebuffer.
+            roofline = the dominant traversal kernel (k_walk closest-hit or shadow), algorithmic bytes
+                     from the reference's own work counts: 48 B/ray + 32 B/box test +
+                     48 B/triangle test, over its CUDA-event time measured on a handle created with
+                     RTB_CREATE_KERNEL_TIMING over the same frames (per-launch events cost stream
+                     time, so `value` is taken on a handle without them).
 reference:  oracle/_ref/ref_driver (the unmodified reference sources, compiled by oracle/Makefile)
             timing launchWorkers + launchSSAA on all host cores; the oracle port when that binary
             is absent.
@@ -44,7 +47,7 @@ L2_FLUSH_BYTES = 256 << 20
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default=DEFAULT_SCENE)
@@ -139,7 +142,7 @@ class ClockSampler:
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.05)
 
     def __enter__(self):
         self.thread.start()
@@ -198,10 +201,10 @@ def ours(args):
     nrows_max = rdist.max_rows(h, args.strip_rows, world)
     out = torch.empty((nrows_max if world > 1 else h, w, 3), dtype=torch.float32, device="cuda")
 
-    def step():
+    def step(rr):
         if world == 1:
-            return r.render_device(out.data_ptr(), stream=stream.cuda_stream), None
-        st = r.render_strips_device(out.data_ptr(), args.strip_rows, rank, world, stream=stream.cuda_stream)
+            return rr.render_device(out.data_ptr(), stream=stream.cuda_stream), None
+        st = rr.render_strips_device(out.data_ptr(), args.strip_rows, rank, world, stream=stream.cuda_stream)
         with torch.cuda.stream(stream):
             frame = rdist.gather_frame(out, h, args.strip_rows, rank, world)
         return st, frame
@@ -212,65 +215,88 @@ def ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
-    kernel_ms = [0.0] * len(KERNEL_KINDS)
-    kernel_launches = [0] * len(KERNEL_KINDS)
-    launches = 0
-    total_ms = 0.0
-    sampler = ClockSampler(local)
-    with sampler:
+    def timed_loop(rr, steps):
+        """K frames, each bracketed by CUDA events on the render stream, L2 flushed (untimed) before each."""
+        total, launches = 0.0, 0
+        kms = [0.0] * len(KERNEL_KINDS)
+        kl = [0] * len(KERNEL_KINDS)
         barrier()
-        for _ in range(args.steps):
+        for _ in range(steps):
             with torch.cuda.stream(stream):
                 flush.zero_()                      # evict L2 (256 MiB written, L2 is 126 MB); not timed
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            st, _ = step()
+            st, _ = step(rr)
             e1.record(stream)
             e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
+            total += e0.elapsed_time(e1)
             launches += st["kernelLaunches"]
             for k in range(len(KERNEL_KINDS)):
-                kernel_ms[k] += st["msKernel"][k]
-                kernel_launches[k] += st["launchesKernel"][k]
+                kms[k] += st["msKernel"][k]
+                kl[k] += st["launchesKernel"][k]
         barrier()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = rays / (ms_per_step * 1e-3) / 1e6
+        return total, launches, kms, kl
 
-    # ---- end to end through the public host-buffer call ----------------------------------------
-    host_fb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
-    host_np = host_fb.numpy()
-    e2e_ms = 0.0
-    h2d = d2h = 0
-    for i in range(args.steps + 1):
-        barrier()
-        t0 = time.perf_counter()
-        if world == 1:
-            _, est = r.render(out=host_np)
-            h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
-        else:
-            est, frame = step()
-            h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
-            if rank == 0:
-                host_fb.copy_(frame, non_blocking=False)
-                d2h_i += host_fb.numel() * 4
-        barrier()
-        if i > 0:
-            e2e_ms += (time.perf_counter() - t0) * 1e3
-            h2d, d2h = h2d_i, d2h_i
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms_per_step = float(te.item()) / args.steps
-    e2e_value = rays / (e2e_ms_per_step * 1e-3) / 1e6
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step(r)
+    barrier()
+
+    sampler = ClockSampler(local)
+    with sampler:
+        total_ms, launches, _, _ = timed_loop(r, args.steps)
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        ms_per_step = total_ms / args.steps
+        value = rays / (ms_per_step * 1e-3) / 1e6
+
+        # ---- per-kernel durations: the same frames on a handle that brackets every launch with CUDA events
+        #      (RTB_CREATE_KERNEL_TIMING; the events themselves cost stream time, so `value` is taken without them)
+        rt_ = rb.Renderer(sc, device=local, kernel_timing=True)
+        for _ in range(warm):
+            step(rt_)
+        ksteps = min(args.steps, 50)
+        ktotal_ms, _, kernel_ms, kernel_launches = timed_loop(rt_, ksteps)
+        rt_.close()
+
+        # ---- end to end through the public host-buffer calls --------------------------------------
+        # headline: rtb_render_bgr8, what Scene::render() calls (the frame arrives as the BMP's pixel bytes);
+        # also reported: rtb_render with a float32 host framebuffer (4x the bytes over PCIe)
+        row_bytes = (w * 3 + 3) & ~3
+        host_px = torch.empty((h, row_bytes), dtype=torch.uint8).pin_memory()
+        host_fb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
+        e2e = {}
+        for name in (("bgr8", "float") if world == 1 else ("float",)):
+            e2e_ms = 0.0
+            h2d = d2h = 0
+            for i in range(args.steps + 2):
+                barrier()
+                t0 = time.perf_counter()
+                if world == 1:
+                    if name == "bgr8":
+                        _, est = r.render_bgr8(out=host_px.numpy())
+                    else:
+                        _, est = r.render(out=host_fb.numpy())
+                    h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
+                else:
+                    est, frame = step(r)
+                    h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
+                    if rank == 0:
+                        host_fb.copy_(frame, non_blocking=False)
+                        d2h_i += host_fb.numel() * 4
+                barrier()
+                if i > 1:
+                    e2e_ms += (time.perf_counter() - t0) * 1e3
+                    h2d, d2h = h2d_i, d2h_i
+            te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            per = float(te.item()) / args.steps
+            e2e[name] = {"value": rays / (per * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": per,
+                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
     if rank != 0:
         if world > 1:
@@ -289,27 +315,38 @@ def ours(args):
     dom = k_trace if kernel_ms[k_trace] >= kernel_ms[k_shadow] else k_shadow
     dom_bytes = (trace_bytes if dom == k_trace else shadow_bytes) / max(1, world)   # per rank share, approx. for N>1
     dom_launches = max(1, kernel_launches[dom])
-    launches_per_step = dom_launches / args.steps
+    launches_per_step = dom_launches / ksteps
     avg_launch_ms = kernel_ms[dom] / dom_launches
     achieved = (dom_bytes / launches_per_step) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+    traffic = None
+    try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr[args.scene]["k_" + KERNEL_KINDS[dom]]["dram_bytes_per_launch"]
+    except Exception:
+        pass
 
+    head = e2e["bgr8"] if e2e.get("bgr8") else e2e["float"]
     line = {
-        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "reference assets (scenes/input: shotgun.obj + three 4096^2 maps), no randomness",
-        "config": {"workload": f"{args.scene}: 1920x1080 frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays,
+        "data": "reference assets (scenes/input), no randomness",
+        "config": {"workload": f"{args.scene}: {w}x{h} frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays,
                    "l2": "flushed between timed frames (256 MiB write)", "partition": f"cyclic strips of {args.strip_rows} rows, 1 gather" if world > 1 else "single GPU",
                    "timing": "CUDA events on the render stream per frame, summed; max over ranks"},
-        "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms_per_step, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "rtb_render with a pinned host framebuffer (the Scene::render() call), wall clock"},
+        "e2e": dict(head, what=("rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes), wall clock"
+                                if e2e.get("bgr8") else "strips rendered per rank, one NCCL gather, frame copied to pinned host memory on rank 0, wall clock")),
+        "e2e_float": e2e["float"] if e2e.get("bgr8") else None,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_" + KERNEL_KINDS[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "k_walk (" + ("closest hit" if dom == k_trace else "shadow / any hit") + ")",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes / launches_per_step, "avg_launch_ms": avg_launch_ms,
                      "launches_per_step": launches_per_step,
-                     "note": "bytes = 48/ray + 32/box test + 48/triangle test with the REFERENCE's work counts (SURVEY.md 8d); "
-                             "the scene is L2-resident, so this is a work-normalised yardstick, not DRAM traffic"},
-        "kernel_ms_per_step": {KERNEL_KINDS[k]: kernel_ms[k] / args.steps for k in range(len(KERNEL_KINDS))},
+                     "note": "bytes = 48/ray + 32/box test + 48/triangle test with the REFERENCE's work counts (SURVEY.md 8d): a work-"
+                             "normalised yardstick, not DRAM traffic (the fast path tests ~1/100 of the reference's triangles and the "
+                             "geometry is L2-resident), hence frac > 1; durations from a handle with per-launch CUDA events "
+                             f"({ksteps} frames, {ktotal_ms / ksteps:.4f} ms/frame with the events)"},
+        "kernel_ms_per_step": {KERNEL_KINDS[k]: kernel_ms[k] / ksteps for k in range(len(KERNEL_KINDS))},
         "clocks": sampler.summary(),
     }
     if args.gpus == 1 and not args.no_cpu_baseline:

@@ -152,7 +152,7 @@ typedef struct RtbStats {
     uint32_t kernelLaunches;
     uint32_t levels;
     float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */
-    float    msKernel[RTB_NKINDS];                /* device time per kernel kind (CUDA events)     */
+    float    msKernel[RTB_NKINDS];                /* device time per kernel kind (RTB_CREATE_KERNEL_TIMING) */
     uint32_t launchesKernel[RTB_NKINDS];
 } RtbStats;
 
@@ -184,6 +184,8 @@ const char* rtb_host_last_error(void);
 #define RTB_CREATE_DEFAULT   0u
 #define RTB_CREATE_COUNTERS  (1u << 0)   /* count box / triangle tests (slower; parity of work)   */
 #define RTB_CREATE_EXACT_WALK (1u << 1)  /* traverse exactly like objects.cpp:587-631 (no culling) */
+#define RTB_CREATE_KERNEL_TIMING (1u << 2) /* fill RtbStats.msKernel: CUDA events around every launch (costs ~6 us
+                                              of stream time per launch, so it is off by default)               */
 
 /* Upload a flattened scene to `device` and build the device acceleration data.                     */
 int  rtb_create(const RtbScene* scene, int device, uint32_t createFlags, RtbHandle** out);

@@ -57,8 +57,9 @@ def build_cuda(force=False):
     out = os.path.join(HERE, "librtb_cuda.so")
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = [os.path.join(CSRC, s) for s in CUDA_DEPS] + [os.path.join(ROOT, "include", "rtb.h")]
-    if force or _stale(out, srcs + deps):
-        _run(["nvcc", *NVCC_FLAGS, *srcs, "-o", out])
+    extra = os.environ.get("RTB_NVCC_EXTRA", "").split()      # experiment knobs, e.g. -DRTB_CHUNK=64
+    if force or extra or _stale(out, srcs + deps):
+        _run(["nvcc", *NVCC_FLAGS, *extra, *srcs, "-o", out])
     return out
 
 

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -80,11 +81,13 @@ struct RtbHandle {
     int smCount = 148;
 
     rt::Scene scene{};                 // header with DEVICE pointers
+    rt::Scene* sceneDev = nullptr;     // the same header resident in HBM
     std::vector<void*> allocations;    // scene-lifetime device allocations
     std::vector<TextureRes> textures;
+    bool kernelTiming = false;         // bracket every launch with CUDA events (RTB_CREATE_KERNEL_TIMING -> RtbStats.msKernel)
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
-    int walkBlocksPerSm[2] = { 1, 1 }; // resident CTAs per SM of k_walk<false> / k_walk<true> with that stack
+    int walkBlocksPerSm[4] = { 1, 1, 1, 1 };   // resident CTAs per SM of k_walk<false, GEN 0..2> / k_walk<true> with that stack
 
     QueueBufs rays[2];
     DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, userRays, outStage;
@@ -189,10 +192,10 @@ int gridFor(const RtbHandle* h, long long n, int block = rtk::kBlock, int perSm 
 
 // persistent kernels: exactly one resident wave (occupancy queried at create time), never more CTAs than
 // the queue's capacity could feed
-int persistentGrid(const RtbHandle* h, bool any, long long cap)
+int persistentGrid(const RtbHandle* h, int variant /* GEN_* or 3 = shadow */, long long cap)
 {
     const long long blocks = (cap + rtk::kBlock - 1) / rtk::kBlock;
-    return (int)std::max(1LL, std::min(blocks, (long long)h->smCount * h->walkBlocksPerSm[any ? 1 : 0]));
+    return (int)std::max(1LL, std::min(blocks, (long long)h->smCount * h->walkBlocksPerSm[variant]));
 }
 
 void launchCheck() { CK(cudaGetLastError()); }
@@ -212,16 +215,18 @@ struct KernelSpan {
     RtbHandle* h; cudaStream_t st; int kind; cudaEvent_t a, b;
     KernelSpan(RtbHandle* h_, cudaStream_t st_, int kind_) : h(h_), st(st_), kind(kind_)
     {
+        if (!h->kernelTiming) return;
         a = takeEvent(h); b = takeEvent(h);
         CK(cudaEventRecord(a, st));
     }
     void done()
     {
         launchCheck();
-        CK(cudaEventRecord(b, st));
-        h->spans.push_back({ kind, a, b });
         h->stats.kernelLaunches++;
         h->stats.launchesKernel[kind]++;
+        if (!h->kernelTiming) return;
+        CK(cudaEventRecord(b, st));
+        h->spans.push_back({ kind, a, b });
     }
 };
 
@@ -265,7 +270,7 @@ void ensureCapacity(RtbHandle* h, cudaStream_t st, long long framePixels, long l
 // Enqueues castRay for the rays sitting in queue 0 of `pass`, level by level, then folds the interior
 // records deepest level first.  Nothing here waits for the device: every kernel reads its work size
 // from the LevelCtr its predecessor filled.
-void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixels)
+void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixels, int genKind = rtk::GEN_QUEUE, rtk::GenArgs gen = rtk::GenArgs{})
 {
     const bool count = h->createFlags & RTB_CREATE_COUNTERS;
     const bool exact = h->createFlags & RTB_CREATE_EXACT_WALK;
@@ -284,12 +289,18 @@ void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixel
             KernelSpan ks(h, st, RTB_K_TRACE);
             if (count) rtk::k_trace<rtk::MODE_COUNT><<<gridFor(h, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, h->dFrame(), lv);
             else if (exact) rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, h->dFrame(), lv);
-            else rtk::k_walk<false><<<persistentGrid(h, false, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv);
+            else if (depth == 0 && genKind == rtk::GEN_PRIMARY)
+                rtk::k_walk<false, rtk::GEN_PRIMARY><<<persistentGrid(h, 1, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
+            else if (depth == 0 && genKind == rtk::GEN_SSAA)
+                rtk::k_walk<false, rtk::GEN_SSAA><<<persistentGrid(h, 2, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
+            else
+                rtk::k_walk<false, rtk::GEN_QUEUE><<<persistentGrid(h, 0, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
             ks.done();
         }
         {
             KernelSpan ks(h, st, RTB_K_SURFACE);
-            rtk::k_surface<<<gridFor(h, cap), rtk::kBlock, 0, st>>>(sc, q, (int)cap, hits, surf, h->slots.as<float>(), lv);
+            const int handleMisses = count || exact || depth > 0 || genKind == rtk::GEN_QUEUE;
+            rtk::k_surface<<<gridFor(h, cap), rtk::kBlock, 0, st>>>(sc, q, (int)cap, hits, surf, h->slots.as<float>(), lv, handleMisses);
             ks.done();
         }
         if (!(sc.flags & rt::FLAG_SHOW_NORMALS)) {
@@ -298,7 +309,7 @@ void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixel
                 KernelSpan ks(h, st, RTB_K_SHADOW);
                 if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, smem, st>>>(sc, q, surf, vis, h->dFrame(), lv);
                 else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, smem, st>>>(sc, q, surf, vis, h->dFrame(), lv);
-                else rtk::k_walk<true><<<persistentGrid(h, true, maxShadow), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv);
+                else rtk::k_walk<true, rtk::GEN_QUEUE><<<persistentGrid(h, 3, maxShadow), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
                 ks.done();
             }
             KernelSpan ks(h, st, RTB_K_SHADE);
@@ -425,13 +436,16 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
         CK(cudaEventRecord(h->ev[0], st));
         CK(cudaMemsetAsync(h->slots.p, 0, (size_t)framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
         CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
+        const bool literalWalk = h->createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK);
         if (n0 > 0) {
-            {
+            if (literalWalk) {   // the literal reference walk reads a materialised queue
                 KernelSpan ks(h, st, RTB_K_RAYGEN);
                 rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)p1rows.size(), h->rays[0].view(), h->dLevel(0, 0));
                 ks.done();
+                enqueueLevels(h, st, 0, framePixels);
+            } else {
+                enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)p1rows.size(), 0, h->slots.as<float>(), h->sceneDev });
             }
-            enqueueLevels(h, st, 0, framePixels);
         }
         CK(cudaEventRecord(h->ev[1], st));
 
@@ -469,13 +483,15 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                 ks.done();
             }
             CK(cudaEventRecord(h->ev[2], st));
-            {
+            if (literalWalk) {
                 KernelSpan ks(h, st, RTB_K_RAYGEN);
                 rtk::k_ssaa_gen<<<gridFor(h, 4 * h->capFlagged), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
                     h->rays[0].view(), h->dFrame(), h->dLevel(1, 0));
                 ks.done();
+                enqueueLevels(h, st, 1, framePixels);
+            } else {
+                enqueueLevels(h, st, 1, framePixels, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, sampleBase, h->slots.as<float>(), h->sceneDev });
             }
-            enqueueLevels(h, st, 1, framePixels);
             KernelSpan ks(h, st, RTB_K_OUTPUT);
             rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
                 h->slots.as<float>(), h->dFrame());
@@ -528,8 +544,8 @@ void enqueueUserRays(RtbHandle* h, cudaStream_t st, const float* rays, int nRays
             if (h->createFlags & (RTB_CREATE_EXACT_WALK | RTB_CREATE_COUNTERS))
                 rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, nRays), rtk::kBlock, stackBytes(h), st>>>(h->scene, h->rays[0].view(), nRays, hits, h->dFrame(), h->dLevel(0, 0));
             else
-                rtk::k_walk<false><<<persistentGrid(h, false, nRays), rtk::kBlock, stackBytes(h), st>>>(h->scene, h->rays[0].view(), nRays, hits,
-                    rtk::SurfQueue{}, nullptr, h->dFrame(), h->dLevel(0, 0));
+                rtk::k_walk<false, rtk::GEN_QUEUE><<<persistentGrid(h, 0, nRays), rtk::kBlock, stackBytes(h), st>>>(h->scene, h->rays[0].view(), nRays, hits,
+                    rtk::SurfQueue{}, nullptr, h->dFrame(), h->dLevel(0, 0), rtk::GenArgs{});
             launchCheck();
         }
         const int overflow = finishFrame(h, st, 1);
@@ -608,6 +624,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         CK(cudaSetDevice(device));
         h->device = device;
         h->createFlags = createFlags;
+        h->kernelTiming = createFlags & RTB_CREATE_KERNEL_TIMING;
         cudaDeviceProp prop{};
         CK(cudaGetDeviceProperties(&prop, device));
         h->smCount = prop.multiProcessorCount;
@@ -639,6 +656,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             if (m.nNodes > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
             meshes.push_back(d);
         }
+        h->sceneDev = upload(h, &h->scene, 1);
         // recursion levels: only Reflective / Transparent hits spawn children (scene.cpp:854-941)
         bool spawns = false;
         for (int i = 0; i < s->nObjects; ++i)
@@ -649,10 +667,11 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         CK(cudaMallocHost(&h->hCtr, h->ctrBytes));
         std::memset(h->hCtr, 0, h->ctrBytes);
         // one resident wave of the persistent traversal kernels with this scene's stack size
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[0], rtk::k_walk<false>, rtk::kBlock, stackBytes(h)));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[1], rtk::k_walk<true>, rtk::kBlock, stackBytes(h)));
-        h->walkBlocksPerSm[0] = std::max(1, h->walkBlocksPerSm[0]);
-        h->walkBlocksPerSm[1] = std::max(1, h->walkBlocksPerSm[1]);
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[0], rtk::k_walk<false, rtk::GEN_QUEUE>, rtk::kBlock, stackBytes(h)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[1], rtk::k_walk<false, rtk::GEN_PRIMARY>, rtk::kBlock, stackBytes(h)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[2], rtk::k_walk<false, rtk::GEN_SSAA>, rtk::kBlock, stackBytes(h)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[3], rtk::k_walk<true, rtk::GEN_QUEUE>, rtk::kBlock, stackBytes(h)));
+        for (int& b : h->walkBlocksPerSm) b = std::max(1, b);
         h->scene.objects = upload(h, objects.data(), objects.size());
         h->scene.lights = upload(h, lights.data(), lights.size());
         h->scene.meshes = upload(h, meshes.data(), meshes.size());

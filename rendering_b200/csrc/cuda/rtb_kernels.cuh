@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int cap,
 // surface stage: castRay between trace() and the light loops (scene.cpp:762-775, 945)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
-    float* __restrict__ slots, LevelCtr* lv)
+    float* __restrict__ slots, LevelCtr* lv, int handleMisses)
 {
     const int n = min(lv->nRays, cap);
     const int nPadded = (n + 31) & ~31;
@@ -252,8 +252,9 @@ __global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int ca
         bool wantSurface = false;
         Surface s;
         int obj = -1;
-        if (i < n && q.dest[i] >= 0) {
-            obj = hits.obj[i];
+        // rays generated inside k_walk resolve their own misses (handleMisses == 0): only obj is valid for those
+        if (i < n) obj = hits.obj[i];
+        if (i < n && (obj >= 0 || (handleMisses && q.dest[i] >= 0))) {
             const float4 d4 = q.d[i];
             const V3 d = mk(d4.x, d4.y, d4.z);
             if (obj < 0) {
@@ -370,31 +371,62 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQue
 // One kernel serves both ray kinds: ANY = false is Render::trace for primary / secondary rays
 // (closest hit over all objects), ANY = true is the shadow trace (any occluder closer than the
 // light, Transparent objects skipped).  The grid is sized to the machine, not to the queue: every
-// warp pulls rays from a global cursor, and whenever fewer than kRefillBelow lanes of a warp still
-// hold a live ray the finished lanes are refilled (ballot + one atomicAdd per warp), so a few long
-// rays never leave the other lanes idle.  Traversal is while-while over the search BVH with the
-// per-thread stack in shared memory.
+// warp pulls rays from a global cursor, and whenever fewer than kRefillBelow lanes of the warp still hold
+// a live ray the finished lanes are refilled (ballot + one atomicAdd per warp), so a few long rays never
+// leave the other lanes idle.
+// Traversal is while-while over the search BVH with the per-thread stack in shared memory.
+//
+// GEN selects where closest-hit rays come from:
+//   GEN_QUEUE    the level's ray queue (secondary rays, caller-supplied rays)
+//   GEN_PRIMARY  generated in place from the pixel grid, 8x4 tiles (renderWorker + Camera::getRay); no queue read
+//   GEN_SSAA     generated in place from the flagged-pixel list, 4 samples per pixel (SSAAworker)
+// Generated rays that miss everything are finished right here (skybox / background colour into the ray's slot);
+// only hits are written to the queue for the surface and shade stages.
 constexpr int kDone = (int)0x80000000;   // cursor value: no mesh traversal in progress
-constexpr int kRefillBelow = 22;
+#ifndef RTB_REFILL_BELOW
+#define RTB_REFILL_BELOW 10
+#endif
+constexpr int kRefillBelow = RTB_REFILL_BELOW;
+enum { GEN_QUEUE = 0, GEN_PRIMARY = 1, GEN_SSAA = 2 };
 
-template <bool ANY>
+struct GenArgs {
+    const int* list;     // GEN_PRIMARY: image rows to render; GEN_SSAA: flagged pixels
+    int count;           // GEN_PRIMARY: number of rows; GEN_SSAA: capacity of the flagged list
+    int slotBase;        // GEN_SSAA: first sample slot
+    float* slots;        // colour slots (misses of generated rays are resolved here)
+    const Scene* scene;  // device-resident copy of the scene header for the out-of-line helpers below
+};
+
+// Kept out of line so their FP64 normalisation / cube-map code does not raise the register count of the
+// traversal loop (they run once per ray, the loop runs ~100 times).
+__device__ __noinline__ V3 genCameraRay(const Scene* sc, float px, float py) { return cameraDir(*sc, px, py); }
+__device__ __noinline__ void storeMissColour(const Scene* sc, float* slots, int dest, V3 d) { storeSlot(slots, dest, skybox(*sc, d)); }
+
+template <bool ANY, int GEN>
 __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
-    unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv)
+    unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv, GenArgs gen)
 {
     extern __shared__ int stackMem[];
     int* stack = stackMem + threadIdx.x;
-    unsigned long long* cursor = &lv->cursor[ANY ? 1 : 0];
-    const int nRays = min(lv->nRays, cap);
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    const unsigned lanesBelow = (1u << lane) - 1;
     const bool cull = sc.flags & FLAG_CULL;
     const int S = sc.shadowRaysPerHit;
+    unsigned long long* cursor = &lv->cursor[ANY ? 1 : 0];
     const int nSurfRaw = ANY ? lv->nSurf : 0;
     const int nSurf = nSurfRaw > 0 ? nSurfRaw : 1;
-    const long long total = ANY ? (long long)nSurfRaw * S : (long long)nRays;
+    long long total;
+    if (ANY) total = (long long)nSurfRaw * S;
+    else if (GEN == GEN_PRIMARY) total = raygenPaddedCount(sc.width, gen.count);
+    else if (GEN == GEN_SSAA) total = 4LL * min(ctr->ssaaPixels, gen.count);
+    else total = min(lv->nRays, cap);
+    if (!ANY && GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
+    const int wm1 = sc.width - 1, tilesX = (wm1 + 7) / 8;
 
     bool have = false, exhausted = false;
     long long out = 0;                 // where the result goes: ray index (closest) or visibility index (ANY)
+    int dest = -1;                     // colour slot of a generated ray
     RayCtx r = makeRay(mk(0.f, 0.f, 0.f), mk(0.f, 0.f, -1.f));
     float tNear = FLT_MAX, uN = -1.f, vN = -1.f;   // best over all objects / light distance
     int objN = -1, triN = -1;
@@ -408,48 +440,77 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
 
     for (;;) {
         // ---- refill idle lanes from the global cursor ----
-        if (!exhausted) {
-            const unsigned idle = __ballot_sync(FULL, !have);
-            if (idle) {
-                const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
-                unsigned long long base = 0;
-                if (lane == leader) base = atomicAdd(cursor, (unsigned long long)nIdle);
-                base = __shfl_sync(FULL, base, leader);
-                if ((long long)base + nIdle >= total) exhausted = true;
-                const long long my = (long long)base + __popc(idle & ((1u << lane) - 1));
-                if (!have && my < total) {
-                    if (!ANY) {
-                        if (q.dest[my] < 0) {
-                            hits.obj[my] = -1;      // padding lane of a ray-generation tile
-                        } else {
-                            const float4 o4 = q.o[my], d4 = q.d[my];
-                            r = makeRay(mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z));
-                            tNear = FLT_MAX; uN = -1.f; vN = -1.f; objN = -1; triN = -1;
-                            out = my; obj = 0; cur = kDone; have = true;
+        // One atomicAdd per refill hands every idle lane the next consecutive ray.  (A per-warp pool of
+        // pre-reserved rays was measured slower: with queues of a few 100k rays the rays parked in the pools
+        // of busy warps are exactly the ones idle warps would need at the tail.)
+        const unsigned idle = __ballot_sync(FULL, !have);
+        if (idle && !exhausted) {
+            const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(cursor, (unsigned long long)nIdle);
+            base = __shfl_sync(FULL, base, leader);
+            if ((long long)base + nIdle >= total) exhausted = true;
+            const long long my = (long long)base + __popc(idle & lanesBelow);
+            const bool take = !have && my < total;
+            if (take) {
+                if (!ANY) {
+                    bool live = true;
+                    V3 o, d;
+                    if (GEN == GEN_PRIMARY) {
+                        const long long tile = my >> 5;
+                        const int x = (int)(tile % tilesX) * 8 + ((int)my & 7);
+                        const int rr = (int)(tile / tilesX) * 4 + (((int)my >> 3) & 3);
+                        live = x < wm1 && rr < gen.count;
+                        if (live) {
+                            const int y = __ldg(gen.list + rr);
+                            o = sc.camPos;
+                            d = genCameraRay(gen.scene, (float)x + 0.5f, (float)y + 0.5f);
+                            dest = y * sc.width + x;
                         }
+                    } else if (GEN == GEN_SSAA) {
+                        const int pix = __ldg(gen.list + (my >> 2)), k = (int)my & 3;
+                        const int y = pix / sc.width, x = pix - y * sc.width;
+                        // sample order (.25,.25) (.25,.75) (.75,.25) (.75,.75)  (scene.cpp:527-534)
+                        const float ox = (k & 2) ? 0.75f : 0.25f, oy = (k & 1) ? 0.75f : 0.25f;
+                        o = sc.camPos;
+                        d = genCameraRay(gen.scene, (float)x + ox, (float)y + oy);
+                        dest = gen.slotBase + (int)my;
                     } else {
-                        // light-major order: neighbouring lanes = neighbouring surfaces, same light sample
-                        const int k = (int)(my / nSurf), si = (int)(my % nSurf);
-                        const float4 p4 = surf.pS[si], n4 = surf.nO[si];
-                        const V3 P = mk(p4.x, p4.y, p4.z), N = mk(n4.x, n4.y, n4.z);
-                        V3 L; float dist;
-                        const bool areaSample = shadowSample(sc, k, P, L, dist);
-                        // dead-ray elision (see k_shadow): the bit cannot influence the pixel
-                        const Object& ob = sc.objects[__float_as_int(n4.w)];
-                        const int mat = ob.material;
-                        bool needed = false;
-                        if (mat == MAT_DIFFUSE || mat == MAT_PHONG) needed = maxf_(0.f, dot(N, -L)) > 0.f;
-                        if (!needed && mat != MAT_DIFFUSE) {
-                            const float4 d4 = q.d[__float_as_int(surf.cR[si].w)];
-                            const float base2 = maxf_(0.f, dot(reflect(L, N), -mk(d4.x, d4.y, d4.z)));
-                            needed = base2 > 0.f || (!areaSample && !(ob.nSpecular > 0.f));
+                        live = q.dest[my] >= 0;      // padding entry
+                        if (live) {
+                            const float4 o4 = q.o[my], d4 = q.d[my];
+                            o = mk(o4.x, o4.y, o4.z); d = mk(d4.x, d4.y, d4.z);
                         }
-                        out = (long long)si * S + k;
-                        if (!needed) { vis[out] = 0; nSkipped++; }
-                        else {
-                            r = makeRay(P + N * sc.bias, -L);
-                            tNear = dist; obj = 0; cur = kDone; have = true;
-                        }
+                    }
+                    if (!live) {
+                        hits.obj[my] = -1;
+                    } else {
+                        r = makeRay(o, d);
+                        tNear = FLT_MAX; uN = -1.f; vN = -1.f; objN = -1; triN = -1;
+                        out = my; obj = 0; cur = kDone; have = true;
+                    }
+                } else {
+                    // light-major order: neighbouring lanes = neighbouring surfaces, same light sample
+                    const int k = (int)(my / nSurf), si = (int)(my % nSurf);
+                    const float4 p4 = surf.pS[si], n4 = surf.nO[si];
+                    const V3 P = mk(p4.x, p4.y, p4.z), N = mk(n4.x, n4.y, n4.z);
+                    V3 L; float dist;
+                    const bool areaSample = shadowSample(sc, k, P, L, dist);
+                    // dead-ray elision (see k_shadow): the bit cannot influence the pixel
+                    const Object& ob = sc.objects[__float_as_int(n4.w)];
+                    const int mat = ob.material;
+                    bool needed = false;
+                    if (mat == MAT_DIFFUSE || mat == MAT_PHONG) needed = maxf_(0.f, dot(N, -L)) > 0.f;
+                    if (!needed && mat != MAT_DIFFUSE) {
+                        const float4 d4 = q.d[__float_as_int(surf.cR[si].w)];
+                        const float base2 = maxf_(0.f, dot(reflect(L, N), -mk(d4.x, d4.y, d4.z)));
+                        needed = base2 > 0.f || (!areaSample && !(ob.nSpecular > 0.f));
+                    }
+                    out = (long long)si * S + k;
+                    if (!needed) { vis[out] = 0; nSkipped++; }
+                    else {
+                        r = makeRay(P + N * sc.bias, -L);
+                        tNear = dist; obj = 0; cur = kDone; have = true;
                     }
                 }
             }
@@ -465,7 +526,19 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
                     // object loop of Render::trace (scene.cpp:731-754)
                     if (obj >= sc.nObjects) {
                         if (ANY) vis[out] = 1;
-                        else { hits.tuv[out] = make_float4(tNear, uN, vN, __int_as_float(triN)); hits.obj[out] = objN; }
+                        else if (GEN == GEN_QUEUE) {
+                            hits.tuv[out] = make_float4(tNear, uN, vN, __int_as_float(triN)); hits.obj[out] = objN;
+                        } else {
+                            hits.obj[out] = objN;
+                            if (objN < 0) {
+                                storeMissColour(gen.scene, gen.slots, dest, r.d);          // castRay's miss branch (scene.cpp:945)
+                            } else {
+                                hits.tuv[out] = make_float4(tNear, uN, vN, __int_as_float(triN));
+                                q.o[out] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
+                                q.d[out] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+                                q.dest[out] = dest;
+                            }
+                        }
                         have = false;
                     } else {
                         const Object& ob = sc.objects[obj];

@@ -61,7 +61,7 @@ def main():
         res["ms_total_exact_walk"] = times
         res["exact_same_as_counted"] = bool((fbx.view(np.uint32) == fb.view(np.uint32)).all())
         r.close()
-        r = rb.Renderer(sc)
+        r = rb.Renderer(sc, kernel_timing=True)
         times = []
         for _ in range(reps):
             fb2, st2 = r.render()

@@ -12,9 +12,9 @@ if [[ " $* " != *" notests "* ]]; then
   echo "pytest exit $?" >> $OUT/${TAG}_pytest.log
   tail -5 $OUT/${TAG}_pytest.log
 fi
-timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+timeout 600 python bench.py --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 tail -c 3000 $OUT/${TAG}_bench.json
-timeout 600 python bench.py --steps 10 --warmup 3 --scene cfgD_dragon_1080 --no-cpu-baseline > $OUT/${TAG}_bench_dragon.json 2> $OUT/${TAG}_bench_dragon.err
+timeout 600 python bench.py --steps 100 --warmup 3 --scene cfgD_dragon_1080 --no-cpu-baseline > $OUT/${TAG}_bench_dragon.json 2> $OUT/${TAG}_bench_dragon.err
 tail -c 1500 $OUT/${TAG}_bench_dragon.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
 tail -c 1000 $OUT/${TAG}_bench_ref.json
