@@ -4,7 +4,7 @@
 // a ray may hit (its "eligibility" semantics are reproduced exactly, see rtb_kernels.cuh) but is a
 // poor search structure: loose boxes, no ordering, leaves of up to 15 756 triangles on the dragon.
 // For speed the kernels search a second structure built here: a binned-SAH BVH2 over the mesh's
-// UNIQUE triangles with tight (slightly padded) boxes and at most 4 triangles per leaf.
+// UNIQUE triangles with tight (slightly padded) boxes and at most `maxLeaf` (default 4) triangles per leaf.
 //
 // Layout (what the GPU reads):
 //   node k = 4 x float4: {c0.lo.xyz, c0.hi.x} {c0.hi.yz, c1.lo.xy} {c1.lo.z, c1.hi.xyz} {child0, child1, -, -}
@@ -45,17 +45,18 @@ struct Result {
     int maxDepth = 0;
 };
 
-constexpr int kMaxLeaf = 4;
+constexpr int kMaxLeafLimit = 8;   // leaf codes keep (count - 1) in 3 bits
 constexpr int kBins = 16;
 
 class Builder {
 public:
     // pos: 9 floats per triangle.  pad: absolute padding added to every leaf-level triangle box so a
     // hit reported by the float Moller-Trumbore test is never culled by the box test.
-    Result build(const float* pos, int nTris, float pad)
+    Result build(const float* pos, int nTris, float pad, int maxLeaf = 4)
     {
         pos_ = pos;
         pad_ = pad;
+        maxLeaf_ = std::min(kMaxLeafLimit, std::max(1, maxLeaf));
         res_ = Result{};
         boxes_.resize(nTris);
         cent_.resize((size_t)nTris * 3);
@@ -88,6 +89,7 @@ public:
 private:
     const float* pos_ = nullptr;
     float pad_ = 0;
+    int maxLeaf_ = 4;
     Result res_;
     std::vector<Box> boxes_;
     std::vector<float> cent_;
@@ -178,7 +180,7 @@ private:
             const int f = ranges[c][0], l = ranges[c][1];
             if (l - f <= 0) { children[c] = ~0; cbox[c] = Box(); continue; }
             cbox[c] = rangeBox(f, l);
-            if (l - f <= kMaxLeaf) {
+            if (l - f <= maxLeaf_) {
                 children[c] = makeLeaf(f, l);
             } else {
                 children[c] = (int)res_.nodes.size();

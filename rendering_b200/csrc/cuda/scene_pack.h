@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -73,7 +74,9 @@ inline void packFastPath(const RtbMesh& m, FastPath& out)
     out.pad = (float)(1e-4 * std::sqrt(diag2)) + 1e-7f;
 
     rtbvh::Builder builder;
-    rtbvh::Result bvh = builder.build(m.pos, m.nTris, out.pad);
+    int maxLeaf = 4;
+    if (const char* e = std::getenv("RTB_BVH_LEAF")) maxLeaf = std::atoi(e);   // tuning knob
+    rtbvh::Result bvh = builder.build(m.pos, m.nTris, out.pad, maxLeaf);
     out.maxDepth = bvh.maxDepth;
     out.nodes.swap(bvh.nodes);
     out.tris.resize(bvh.triOrder.size() * 3);
