@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--scene", default=DEFAULT_SCENE)
     ap.add_argument("--strip-rows", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1: how the strips reach rank 0 (p2p = NVLink stores into rank 0's symmetric-memory frame)")
     return ap.parse_args()
 
 
@@ -198,16 +200,13 @@ def ours(args):
     shadow_bytes = 48 * cst["shadowRays"] + 32 * cst["boxTestsShadow"] + 48 * cst["triTestsShadow"]
 
     r = rb.Renderer(sc, device=local)
-    nrows_max = rdist.max_rows(h, args.strip_rows, world)
-    out = torch.empty((nrows_max if world > 1 else h, w, 3), dtype=torch.float32, device="cuda")
+    out = torch.empty((h, w, 3), dtype=torch.float32, device="cuda") if world == 1 else None
+    exchange = rdist.FrameExchange(h, w, args.strip_rows, rank, world, torch.device("cuda", local), args.transport) if world > 1 else None
 
     def step(rr):
         if world == 1:
             return rr.render_device(out.data_ptr(), stream=stream.cuda_stream), None
-        st = rr.render_strips_device(out.data_ptr(), args.strip_rows, rank, world, stream=stream.cuda_stream)
-        with torch.cuda.stream(stream):
-            frame = rdist.gather_frame(out, h, args.strip_rows, rank, world)
-        return st, frame
+        return exchange.render(rr, stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -269,7 +268,7 @@ def ours(args):
         host_px = torch.empty((h, row_bytes), dtype=torch.uint8).pin_memory()
         host_fb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
         e2e = {}
-        for name in (("bgr8", "float") if world == 1 else ("float",)):
+        for name in ("bgr8", "float"):
             e2e_ms = 0.0
             h2d = d2h = 0
             for i in range(args.steps + 2):
@@ -285,8 +284,13 @@ def ours(args):
                     est, frame = step(r)
                     h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
                     if rank == 0:
-                        host_fb.copy_(frame, non_blocking=False)
-                        d2h_i += host_fb.numel() * 4
+                        stream.synchronize()
+                        if name == "bgr8":
+                            r.frame_to_bgr8(frame.data_ptr(), host_px.numpy())
+                            d2h_i += host_px.numel()
+                        else:
+                            host_fb.copy_(frame, non_blocking=False)
+                            d2h_i += host_fb.numel() * 4
                 barrier()
                 if i > 1:
                     e2e_ms += (time.perf_counter() - t0) * 1e3
@@ -331,10 +335,10 @@ def ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference assets (scenes/input), no randomness",
         "config": {"workload": f"{args.scene}: {w}x{h} frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays,
-                   "l2": "flushed between timed frames (256 MiB write)", "partition": f"cyclic strips of {args.strip_rows} rows, 1 gather" if world > 1 else "single GPU",
+                   "l2": "flushed between timed frames (256 MiB write)", "partition": (f"cyclic strips of {args.strip_rows} rows; exchange: " + ("NVLink stores into rank 0's symmetric-memory frame + 1 device barrier" if exchange.transport == "p2p" else "1 NCCL gather")) if world > 1 else "single GPU",
                    "timing": "CUDA events on the render stream per frame, summed; max over ranks"},
         "e2e": dict(head, what=("rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes), wall clock"
-                                if e2e.get("bgr8") else "strips rendered per rank, one NCCL gather, frame copied to pinned host memory on rank 0, wall clock")),
+                                if world == 1 else f"strips rendered per rank, exchanged to rank 0 ({exchange.transport}), converted to BMP pixel bytes there and copied to pinned host memory, wall clock")),
         "e2e_float": e2e["float"] if e2e.get("bgr8") else None,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_walk (" + ("closest hit" if dom == k_trace else "shadow / any hit") + ")",

@@ -210,6 +210,13 @@ int  rtb_render_bgr8(RtbHandle* h, int y0, int y1, uint8_t* bgr, int onDevice, v
  * *nRowsOut.  One halo row either side of every strip is rendered locally for the Sobel window.    */
 int  rtb_render_strips(RtbHandle* h, int stripRows, int rank, int worldSize, float* fb,
                        int fbOnDevice, void* stream, int* nRowsOut, RtbStats* stats);
+/* Same partition, but every owned row y is written at frame + y*width*3 of a FULL-FRAME device buffer.  `frame`
+ * may be a peer-mapped pointer to the root rank's framebuffer (CUDA IPC / symmetric memory over NVLink): the strips
+ * then land in place through the output kernel's own stores and no separate gather or un-permute runs.  The caller
+ * synchronises the ranks afterwards (a barrier).                                                                    */
+int  rtb_render_strips_to_frame(RtbHandle* h, int stripRows, int rank, int worldSize, float* frame, void* stream, RtbStats* stats);
+/* saveImage's conversion (see rtb_render_bgr8) of an assembled full float frame resident on the handle's device.    */
+int  rtb_frame_to_bgr8(RtbHandle* h, const float* frame, uint8_t* bgr, int onDevice, void* stream);
 /* Number of rows rank owns under that partition (for sizing buffers).                              */
 int  rtb_strip_rows_owned(int height, int stripRows, int rank, int worldSize);
 

@@ -84,7 +84,7 @@ KERNEL_KINDS = ["raygen", "trace", "surface", "shadow", "shade", "combine", "sob
 # every symbol include/rtb.h declares, by library (tests check both lists against the header)
 HOST_SYMBOLS = ["rtb_scene_load", "rtb_scene_parse", "rtb_scene_view", "rtb_scene_image_name", "rtb_scene_free",
                 "rtb_scene_tree_stats", "rtb_save_bmp", "rtb_save_bmp_bgr8", "rtb_host_last_error"]
-CUDA_SYMBOLS = ["rtb_create", "rtb_render", "rtb_render_bgr8", "rtb_render_strips", "rtb_strip_rows_owned", "rtb_trace", "rtb_cast",
+CUDA_SYMBOLS = ["rtb_create", "rtb_render", "rtb_render_bgr8", "rtb_render_strips", "rtb_render_strips_to_frame", "rtb_frame_to_bgr8", "rtb_strip_rows_owned", "rtb_trace", "rtb_cast",
                 "rtb_device_of", "rtb_destroy", "rtb_last_error", "rtb_abi_version"]
 
 _host = None
@@ -136,6 +136,10 @@ def cuda_lib():
         lib.rtb_render_bgr8.restype = C.c_int
         lib.rtb_render_strips.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(RtbStats)]
         lib.rtb_render_strips.restype = C.c_int
+        lib.rtb_render_strips_to_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(RtbStats)]
+        lib.rtb_render_strips_to_frame.restype = C.c_int
+        lib.rtb_frame_to_bgr8.argtypes = [vp, vp, vp, C.c_int, vp]
+        lib.rtb_frame_to_bgr8.restype = C.c_int
         lib.rtb_strip_rows_owned.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         lib.rtb_strip_rows_owned.restype = C.c_int
         lib.rtb_trace.argtypes = [vp, vp, C.c_int, vp, vp]

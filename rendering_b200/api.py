@@ -160,6 +160,18 @@ class Renderer:
         d["rows"] = n.value
         return d
 
+    def render_strips_to_frame(self, frame_ptr: int, strip_rows: int, rank: int, world: int, stream: int | None = None) -> dict:
+        """Owned rows written at their image position of a full-frame device buffer (may be a peer-mapped pointer)."""
+        st = _ffi.RtbStats()
+        self._check(self._lib.rtb_render_strips_to_frame(self._h, strip_rows, rank, world, C.c_void_p(frame_ptr),
+                                                         C.c_void_p(stream) if stream else None, C.byref(st)))
+        return st.as_dict()
+
+    def frame_to_bgr8(self, frame_ptr: int, out: np.ndarray, stream: int | None = None) -> None:
+        """saveImage's conversion of an assembled float frame on this handle's device into host pixel bytes."""
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self.height * ((self.width * 3 + 3) & ~3)
+        self._check(self._lib.rtb_frame_to_bgr8(self._h, C.c_void_p(frame_ptr), out.ctypes.data, 0, C.c_void_p(stream) if stream else None))
+
     def render_strips(self, strip_rows: int, rank: int, world: int):
         n = self.rows_owned(strip_rows, rank, world)
         fb = np.empty((n, self.width, 3), np.float32)

@@ -382,7 +382,7 @@ void growAfterOverflow(RtbHandle* h, int bits, int passes)
     if (bits & rtk::OVF_INTERIORS) h->capInterior = std::max(2 * h->capInterior, (long long)h->hFrame()->interiors);
 }
 
-enum OutputKind { OUT_FLOAT = 0, OUT_BGR8 = 1 };
+enum OutputKind { OUT_FLOAT = 0, OUT_BGR8 = 1, OUT_SCATTER = 2 };   // OUT_SCATTER: rows go to their image position of a full-frame device buffer
 
 void uploadRows(RtbHandle* h, cudaStream_t st, DevBuf& buf, std::vector<int>& resident, const std::vector<int>& rows)
 {
@@ -462,7 +462,10 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                 CK(cudaMemcpyAsync(dst, src, bytes, fbOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
             } else {
                 KernelSpan ks(h, st, RTB_K_OUTPUT);
-                if (k == OUT_BGR8)
+                if (k == OUT_SCATTER)
+                    rtk::k_scatter_rows<<<gridFor(h, (long long)(bytes / 16)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                        (int)owned.size(), static_cast<float*>(target));
+                else if (k == OUT_BGR8)
                     rtk::k_quantize_bgr8<<<gridFor(h, (long long)(bytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
                         (int)owned.size(), static_cast<unsigned int*>(target));
                 else
@@ -722,6 +725,39 @@ int rtb_render_strips(RtbHandle* h, int stripRowsN, int rank, int worldSize, flo
         const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize);
         if (nRowsOut) *nRowsOut = (int)rows.size();
         return renderRows(h, rows, fb, nullptr, fbOnDevice, stream, stats);
+    });
+}
+
+int rtb_render_strips_to_frame(RtbHandle* h, int stripRowsN, int rank, int worldSize, float* frame, void* stream, RtbStats* stats)
+{
+    if (!h || !frame) { g_err = "null argument"; return RTB_ERR_ARG; }
+    if (stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) { g_err = "bad strip partition"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize);
+        return renderRows(h, rows, frame, nullptr, 1, stream, stats, OUT_SCATTER);
+    });
+}
+
+int rtb_frame_to_bgr8(RtbHandle* h, const float* frame, uint8_t* bgr, int onDevice, void* stream)
+{
+    if (!h || !frame || !bgr) { g_err = "null argument"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        CK(cudaSetDevice(h->device));
+        cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
+        const int w = h->scene.width, ht = h->scene.height;
+        std::vector<int> rows(ht);
+        for (int y = 0; y < ht; ++y) rows[y] = y;
+        RtbStats keep = h->stats;
+        uploadRows(h, st, h->rowsB, h->rowsBHost, rows);
+        h->stats = keep;
+        const size_t bytes = (size_t)ht * ((w * 3 + 3) & ~3);
+        void* target = bgr;
+        if (!onDevice) { h->outStage.reserve(bytes, st, false); target = h->outStage.p; }
+        rtk::k_quantize_bgr8<<<gridFor(h, (long long)(bytes / 4)), rtk::kBlock, 0, st>>>(frame, w, h->rowsB.as<int>(), ht, static_cast<unsigned int*>(target));
+        launchCheck();
+        if (!onDevice) CK(cudaMemcpyAsync(bgr, target, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return RTB_OK;
     });
 }
 

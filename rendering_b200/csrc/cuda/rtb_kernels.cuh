@@ -874,6 +874,31 @@ __global__ void k_gather_rows(const float* __restrict__ fb, int width, const int
     }
 }
 
+// Same rows, but written at their IMAGE position of a full-frame buffer: out may be a peer-mapped pointer to
+// another GPU's framebuffer (NVLink stores), which makes this kernel the gather of the multi-GPU frame.
+__global__ void k_scatter_rows(const float* __restrict__ fb, int width, const int* __restrict__ rows, int nRows, float* __restrict__ out)
+{
+    const int rowFloats = width * 3;
+    if ((rowFloats & 3) == 0 && (((size_t)fb | (size_t)out) & 15) == 0) {
+        const int rowVecs = rowFloats >> 2;
+        const long long total = (long long)nRows * rowVecs;
+        const float4* src = reinterpret_cast<const float4*>(fb);
+        float4* dst = reinterpret_cast<float4*>(out);
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int r = (int)(i / rowVecs);
+            const long long at = (long long)rows[r] * rowVecs + (i - (long long)r * rowVecs);
+            dst[at] = src[at];
+        }
+        return;
+    }
+    const long long total = (long long)nRows * rowFloats;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / rowFloats);
+        const long long at = (long long)rows[r] * rowFloats + (i % rowFloats);
+        out[at] = fb[at];
+    }
+}
+
 // saveImage's pixel conversion on the device (util.cpp:46-56): rows bottom-up, B,G,R byte order, each channel
 // (uint8)(clamp(0,1,v)*255), rows padded to a multiple of 4 bytes.  Output row j holds image row rows[nRows-1-j].
 // One thread converts 4 bytes (= 4 channels) and stores them as one 32-bit word.

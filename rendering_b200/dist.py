@@ -1,4 +1,4 @@
-"""Multi-GPU plumbing: pixel-strip partition of one frame and the single gather of the framebuffer.
+"""Multi-GPU plumbing: pixel-strip partition of one frame and the single exchange of the framebuffer.
 
 The reference parallelises a frame over 128x128 tiles on std::threads sharing one scene
 (src/scene.cpp:470-506).  Here the scene is replicated on every GPU, image rows are dealt out in
@@ -41,3 +41,66 @@ def gather_frame(local: torch.Tensor, height: int, strip_rows: int, rank: int, w
         rows = torch.as_tensor(owned_rows(height, strip_rows, r, world), device=local.device, dtype=torch.long)
         frame.index_copy_(0, rows, bufs[r][: len(rows)])
     return frame
+
+
+class FrameExchange:
+    """Assembles the strips of all ranks into one frame on rank 0, once per frame.
+
+    Preferred transport ("p2p"): rank 0's framebuffer lives in symmetric memory
+    (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every rank over NVLink), every rank's
+    output kernel stores its rows straight into it at their image position (rtb_render_strips_to_frame with the
+    peer pointer), and one device-side barrier on the render stream closes the frame: the transfer is the output
+    kernel's own stores, there is no separate collective and no un-permute.
+    Fallback ("nccl"): compact per-rank buffers, one torch.distributed.gather over NCCL, rows put back in image
+    order with preallocated index tensors (gather_frame above, without its per-call allocations).
+    """
+
+    def __init__(self, height: int, width: int, strip_rows: int, rank: int, world: int, device, transport: str = "auto"):
+        self.h, self.w, self.strip, self.rank, self.world = height, width, strip_rows, rank, world
+        self.device = torch.device(device)
+        self.transport = "nccl"
+        self.frame = None
+        if transport in ("auto", "p2p") and world > 1 and self.device.type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.frame = symm_mem.empty((height, width, 3), dtype=torch.float32, device=self.device)
+                self.hdl = symm_mem.rendezvous(self.frame, dist.group.WORLD)
+                self.root_ptr = int(self.hdl.buffer_ptrs[0])
+                self.transport = "p2p"
+            except Exception as e:   # no VMM / fabric handle support on this box: use the collective
+                if transport == "p2p":
+                    raise
+                self.why_not_p2p = repr(e)
+                self.frame = None
+        # every rank must agree on the transport
+        if world > 1:
+            flag = torch.tensor([1 if self.transport == "p2p" else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.transport = "nccl"
+        if self.transport == "nccl":
+            self.local = torch.empty((max_rows(height, strip_rows, world), width, 3), dtype=torch.float32, device=self.device)
+            if rank == 0:
+                self.bufs = [torch.empty_like(self.local) for _ in range(world)]
+                self.rows = [torch.as_tensor(owned_rows(height, strip_rows, r, world), device=self.device, dtype=torch.long) for r in range(world)]
+                if self.frame is None:
+                    self.frame = torch.empty((height, width, 3), dtype=torch.float32, device=self.device)
+
+    def render(self, renderer, stream):
+        """Render this rank's strips and exchange.  Returns (stats, frame on rank 0 / None elsewhere).  Everything is
+        enqueued on `stream` (a torch.cuda.Stream)."""
+        import contextlib
+        on = (lambda: torch.cuda.stream(stream)) if self.device.type == "cuda" else contextlib.nullcontext
+        raw = stream.cuda_stream if self.device.type == "cuda" else None
+        if self.transport == "p2p":
+            st = renderer.render_strips_to_frame(self.root_ptr, self.strip, self.rank, self.world, stream=raw)
+            with on():
+                self.hdl.barrier(channel=0)
+            return st, (self.frame if self.rank == 0 else None)
+        st = renderer.render_strips_device(self.local.data_ptr(), self.strip, self.rank, self.world, stream=raw)
+        with on():
+            dist.gather(self.local, self.bufs if self.rank == 0 else None, dst=0)
+            if self.rank == 0:
+                for r in range(self.world):
+                    self.frame.index_copy_(0, self.rows[r], self.bufs[r][: len(self.rows[r])])
+        return st, (self.frame if self.rank == 0 else None)

@@ -143,6 +143,24 @@ def test_row_ranges_and_strips_reassemble_to_the_full_frame():
         assert np.array_equal(frame.view(np.uint32), full.view(np.uint32)), (strip, world)
 
 
+def test_strips_written_in_place_assemble_the_frame():
+    # rtb_render_strips_to_frame: every rank's rows land at their image position of ONE full-frame buffer (the multi-GPU
+    # exchange writes rank 0's frame through a peer pointer; here all "ranks" run on one device)
+    sc = rb.Scene(text=MIXED_SCENE.replace("width=96", "width=120").replace("height=64", "height=77"))
+    r = rb.Renderer(sc)
+    full, _ = r.render()
+    px_full, _ = r.render_bgr8()
+    for strip, world in [(8, 2), (5, 3), (1, 4)]:
+        frame = torch.full((sc.height, sc.width, 3), -7.0, dtype=torch.float32, device="cuda:0")
+        for rank in range(world):
+            r.render_strips_to_frame(frame.data_ptr(), strip, rank, world)
+        torch.cuda.synchronize()
+        assert np.array_equal(frame.cpu().numpy().view(np.uint32), full.view(np.uint32)), (strip, world)
+        px = np.empty_like(px_full)
+        r.frame_to_bgr8(frame.data_ptr(), px)
+        assert np.array_equal(px, px_full)
+
+
 def test_device_buffer_path_matches_host_buffer_path():
     sc = rb.Scene(text=MIXED_SCENE)
     r = rb.Renderer(sc)

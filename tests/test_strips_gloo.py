@@ -48,3 +48,39 @@ def test_gather_frame_gloo(tmp_path, world, height, strip):
     port = 29500 + (os.getpid() % 2000) + world
     mp.spawn(_worker, args=(world, port, height, 16, strip, str(tmp_path)), nprocs=world, join=True)
     assert (tmp_path / "ok").exists()
+
+
+class _FakeRenderer:
+    """Stands in for rb.Renderer on the CPU box: fills the compact buffer the way rtb_render_strips would."""
+
+    def __init__(self, full, exchange):
+        self.full, self.ex = full, exchange
+
+    def render_strips_device(self, ptr, strip, rank, world, stream=None):
+        assert ptr == self.ex.local.data_ptr()
+        rows = rdist.owned_rows(self.full.shape[0], strip, rank, world)
+        self.ex.local[: len(rows)] = self.full[torch.as_tensor(rows)]
+        return {"rows": len(rows)}
+
+
+def _exchange_worker(rank, world, port, height, width, strip, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(height * width * 3, dtype=torch.float32).reshape(height, width, 3)
+    ex = rdist.FrameExchange(height, width, strip, rank, world, "cpu")
+    assert ex.transport == "nccl"          # the collective path (gloo here); p2p needs CUDA symmetric memory
+    for _ in range(2):                     # buffers are reused frame after frame
+        st, frame = ex.render(_FakeRenderer(full, ex), None)
+        assert (frame is not None) == (rank == 0)
+        if rank == 0:
+            assert torch.equal(frame, full)
+    if rank == 0:
+        open(os.path.join(out_dir, "ok"), "w").write("1")
+    dist.destroy_process_group()
+
+
+def test_frame_exchange_collective_path_gloo(tmp_path):
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_exchange_worker, args=(2, port, 37, 16, 8, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").exists()
