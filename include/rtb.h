@@ -175,6 +175,10 @@ void rtb_scene_free(RtbHostScene* hs);
 int  rtb_scene_tree_stats(const RtbHostScene* hs, int mesh, int64_t out[6]);
 /* saveImage contract (util.cpp:15-76) with the well-defined quantisation (uint8)(clamp(v)*255).    */
 int  rtb_save_bmp(const char* path, const float* fb, int width, int height);
+/* Camera constants for a position / Euler rotation (degrees) / field of view, computed exactly like the loader does
+ * for the [options] keys position, rotation, fov (scene.cpp:170-171,182-185 -> Camera::getRay :24-48, renderWorker :447-448).
+ * Feed the result to rtb_set_camera to move the camera of a resident scene between frames.                          */
+int  rtb_camera_from_angles(const float pos[3], const float rotDeg[3], float fovDeg, int width, int height, RtbCamera* out);
 /* Writes header + the pixel bytes produced by rtb_render_bgr8 for the full frame.                   */
 int  rtb_save_bmp_bgr8(const char* path, const uint8_t* bgr, int width, int height);
 const char* rtb_host_last_error(void);
@@ -190,6 +194,10 @@ const char* rtb_host_last_error(void);
 /* Upload a flattened scene to `device` and build the device acceleration data.                     */
 int  rtb_create(const RtbScene* scene, int device, uint32_t createFlags, RtbHandle** out);
 
+/* Replace the camera of a resident scene (the reference is single-shot: one Scene, one render(); a persistent handle
+ * renders a camera sweep without re-uploading geometry or textures).  Takes effect from the next rtb_render* call.   */
+int  rtb_set_camera(RtbHandle* h, const RtbCamera* camera);
+
 /* Render rows [y0,y1) of the frame: pass 1 (launchWorkers) + Sobel + SSAA (launchSSAA), with the
  * reference's quirks (last row/column black, pixel centre x+1.0, Sobel over unclamped floats).
  * `fb` receives (y1-y0)*width*3 floats, row y0 first; it is a HOST pointer (copied back inside the
@@ -204,6 +212,11 @@ int  rtb_render(RtbHandle* h, int y0, int y1, float* fb, float* pass1, int fbOnD
  * to a multiple of 4 bytes — (y1-y0) * ((3*width+3)&~3) bytes.  The conversion runs on the device, so a host
  * buffer (onDevice == 0) receives a quarter of the bytes rtb_render copies back.                            */
 int  rtb_render_bgr8(RtbHandle* h, int y0, int y1, uint8_t* bgr, int onDevice, void* stream, RtbStats* stats);
+
+/* The showAC debug view (options::showAC, scene.cpp:607-635): fb = per-pixel count of reference-tree boxes passed by
+ * the primary ray's line (Scene::countAC :659-669) / the largest count, on all three channels; every pixel of the
+ * frame, pixel centre x+0.5.  `counts` (optional, width*height int32) receives the raw counts.                      */
+int  rtb_render_ac(RtbHandle* h, float* fb, int32_t* counts, int onDevice, void* stream, RtbStats* stats);
 
 /* Render the rows owned by `rank` under a cyclic strip partition: strip s (stripRows rows) belongs
  * to rank s % worldSize.  Output is compact: owned rows in ascending order; returns their count in

@@ -16,6 +16,7 @@
 //   ref_driver tree   <scene> <out.bin>                per-mesh tree + triangle dump (DFS pre-order)
 //   ref_driver cast   <scene> <rays.f32> <out.f32>     Render::castRay on caller-supplied rays
 //   ref_driver stats  <scene> [workers]                reference's own counters (collectStatistics)
+//   ref_driver ac     <scene> <out.i32>                per-pixel Scene::countAC of the showAC debug view (scene.cpp:607-635)
 #include "scene.h"
 #include "stats.h"
 #include "util.h"
@@ -231,6 +232,29 @@ int main(int argc, char** argv)
 			(int)stats::raysCasted, (int)stats::accelStructTests, (int)stats::rayTriTests,
 			(size_t)stats::triCopiesCount, (size_t)stats::meshCount);
 		delete[] fb;
+	}
+	else if (mode == "ac") {
+		if (argc < 4) return 2;
+		// the showAC branch of Scene::render() keeps its counts private and only writes the 8-bit BMP; drive the
+		// same public calls (Camera::getRay, Scene::countAC) over the same pixel grid and dump the integers
+		const float scale = tanf(s.camera.fov * 0.5f / 180.0f * (float)(M_PI));
+		const float aspect = (s.options.width) / (float)s.options.height;
+		std::vector<int> counts(w * h);
+		int acMax = 0;
+		for (size_t y = 0; y < h; y++)
+			for (size_t x = 0; x < w; x++) {
+				float xPix = (2 * (x + 0.5f) / (float)w - 1) * scale * aspect;
+				float yPix = -(2 * (y + 0.5f) / (float)h - 1) * scale;
+				Ray ray = s.camera.getRay(xPix, yPix);
+				int val = s.countAC(ray);
+				if (val > acMax) acMax = val;
+				counts[x + y * w] = val;
+			}
+		FILE* f = fopen(argv[3], "wb");
+		if (!f) return 2;
+		fwrite(counts.data(), 4, counts.size(), f);
+		fclose(f);
+		printf("{\"width\": %zu, \"height\": %zu, \"ac_max\": %d}\n", w, h, acMax);
 	}
 	else {
 		fprintf(stderr, "unknown mode %s\n", mode.c_str());

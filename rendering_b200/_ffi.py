@@ -83,8 +83,8 @@ KERNEL_KINDS = ["raygen", "trace", "surface", "shadow", "shade", "combine", "sob
 
 # every symbol include/rtb.h declares, by library (tests check both lists against the header)
 HOST_SYMBOLS = ["rtb_scene_load", "rtb_scene_parse", "rtb_scene_view", "rtb_scene_image_name", "rtb_scene_free",
-                "rtb_scene_tree_stats", "rtb_save_bmp", "rtb_save_bmp_bgr8", "rtb_host_last_error"]
-CUDA_SYMBOLS = ["rtb_create", "rtb_render", "rtb_render_bgr8", "rtb_render_strips", "rtb_render_strips_to_frame", "rtb_frame_to_bgr8", "rtb_strip_rows_owned", "rtb_trace", "rtb_cast",
+                "rtb_scene_tree_stats", "rtb_camera_from_angles", "rtb_save_bmp", "rtb_save_bmp_bgr8", "rtb_host_last_error"]
+CUDA_SYMBOLS = ["rtb_create", "rtb_set_camera", "rtb_render", "rtb_render_bgr8", "rtb_render_ac", "rtb_render_strips", "rtb_render_strips_to_frame", "rtb_frame_to_bgr8", "rtb_strip_rows_owned", "rtb_trace", "rtb_cast",
                 "rtb_device_of", "rtb_destroy", "rtb_last_error", "rtb_abi_version"]
 
 _host = None
@@ -112,6 +112,8 @@ def host_lib():
         lib.rtb_scene_tree_stats.restype = C.c_int
         lib.rtb_save_bmp.argtypes = [C.c_char_p, C.POINTER(f32), C.c_int, C.c_int]
         lib.rtb_save_bmp.restype = C.c_int
+        lib.rtb_camera_from_angles.argtypes = [C.POINTER(f32), C.POINTER(f32), f32, C.c_int, C.c_int, C.POINTER(RtbCamera)]
+        lib.rtb_camera_from_angles.restype = C.c_int
         lib.rtb_save_bmp_bgr8.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
         lib.rtb_save_bmp_bgr8.restype = C.c_int
         lib.rtb_host_last_error.argtypes = []
@@ -132,8 +134,12 @@ def cuda_lib():
         lib.rtb_create.restype = C.c_int
         lib.rtb_render.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.POINTER(RtbStats)]
         lib.rtb_render.restype = C.c_int
+        lib.rtb_set_camera.argtypes = [vp, C.POINTER(RtbCamera)]
+        lib.rtb_set_camera.restype = C.c_int
         lib.rtb_render_bgr8.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(RtbStats)]
         lib.rtb_render_bgr8.restype = C.c_int
+        lib.rtb_render_ac.argtypes = [vp, vp, vp, C.c_int, vp, C.POINTER(RtbStats)]
+        lib.rtb_render_ac.restype = C.c_int
         lib.rtb_render_strips.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(RtbStats)]
         lib.rtb_render_strips.restype = C.c_int
         lib.rtb_render_strips_to_frame.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(RtbStats)]

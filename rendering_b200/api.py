@@ -130,6 +130,23 @@ class Renderer:
         self._check(self._lib.rtb_render(self._h, y0, y1, fb.ctypes.data, p1.ctypes.data if want_pass1 else None, 0, None, C.byref(st)))
         return (fb, p1, st.as_dict()) if want_pass1 else (fb, st.as_dict())
 
+    def set_camera(self, position=(0.0, 0.0, 0.0), rotation=(0.0, 0.0, 0.0), fov: float = 60.0) -> None:
+        """Move the camera of the resident scene (degrees, like the .scene keys position / rotation / fov)."""
+        cam = _ffi.RtbCamera()
+        host = _ffi.host_lib()
+        rc = host.rtb_camera_from_angles((C.c_float * 3)(*position), (C.c_float * 3)(*rotation), fov, self.width, self.height, C.byref(cam))
+        if rc != _ffi.RTB_OK:
+            raise RtbError(rc, host.rtb_host_last_error().decode())
+        self._check(self._lib.rtb_set_camera(self._h, C.byref(cam)))
+
+    def render_ac(self):
+        """showAC debug view: (float32 frame (h, w, 3), int32 box counts (h, w), stats)."""
+        fb = np.empty((self.height, self.width, 3), np.float32)
+        counts = np.empty((self.height, self.width), np.int32)
+        st = _ffi.RtbStats()
+        self._check(self._lib.rtb_render_ac(self._h, fb.ctypes.data, counts.ctypes.data, 0, None, C.byref(st)))
+        return fb, counts, st.as_dict()
+
     def render_bgr8(self, y0: int = 0, y1: int | None = None, out: np.ndarray | None = None):
         """The frame as saveImage's pixel bytes (src/util.cpp:46-56): uint8 (rows, row_bytes), bottom-up, B,G,R,
         rows padded to 4 bytes; converted on the device."""

@@ -85,6 +85,7 @@ struct RtbHandle {
     std::vector<void*> allocations;    // scene-lifetime device allocations
     std::vector<TextureRes> textures;
     bool kernelTiming = false;         // bracket every launch with CUDA events (RTB_CREATE_KERNEL_TIMING -> RtbStats.msKernel)
+    std::vector<int> refTreeDepth;     // depth of every mesh's reference tree (showAC walk)
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
     int walkBlocksPerSm[4] = { 1, 1, 1, 1 };   // resident CTAs per SM of k_walk<false, GEN 0..2> / k_walk<true> with that stack
@@ -655,6 +656,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             d.normal = uploadImage(h, m.normalMap);
             d.specular = uploadImage(h, m.specularMap);
             d.nNodes = m.nNodes; d.nSlots = m.nRefs; d.nTris = m.nTris; d.maxDepth = pm.maxDepth;
+            h->refTreeDepth.push_back(pm.maxDepth);
             if (createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK)) h->stackEntries = std::max(h->stackEntries, pm.maxDepth + 1);
             if (m.nNodes > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
             meshes.push_back(d);
@@ -688,6 +690,21 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
     return RTB_OK;
 }
 
+int rtb_set_camera(RtbHandle* h, const RtbCamera* camera)
+{
+    if (!h || !camera) { g_err = "null argument"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        CK(cudaSetDevice(h->device));
+        h->scene.camPos = rtpack::v3of(camera->pos);
+        for (int i = 0; i < 16; ++i) h->scene.camM[i] = camera->rMatrix[i];
+        h->scene.camScale = camera->scale;
+        h->scene.camAspect = camera->aspect;
+        CK(cudaStreamSynchronize(h->ownStream));
+        CK(cudaMemcpy(h->sceneDev, &h->scene, sizeof(rt::Scene), cudaMemcpyHostToDevice));
+        return RTB_OK;
+    });
+}
+
 int rtb_render(RtbHandle* h, int y0, int y1, float* fb, float* pass1, int fbOnDevice, void* stream, RtbStats* stats)
 {
     if (!h || !fb) { g_err = "null argument"; return RTB_ERR_ARG; }
@@ -707,6 +724,45 @@ int rtb_render_bgr8(RtbHandle* h, int y0, int y1, uint8_t* bgr, int onDevice, vo
         std::vector<int> rows;
         for (int y = y0; y < y1; ++y) rows.push_back(y);
         return renderRows(h, rows, bgr, nullptr, onDevice, stream, stats, OUT_BGR8);
+    });
+}
+
+int rtb_render_ac(RtbHandle* h, float* fb, int32_t* counts, int onDevice, void* stream, RtbStats* stats)
+{
+    if (!h || !fb) { g_err = "null argument"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
+        beginCall(h);
+        const int total = h->scene.width * h->scene.height;
+        // the walk follows the REFERENCE tree, whose depth bounds the stack
+        int depth = 1;
+        for (int d : h->refTreeDepth) depth = std::max(depth, d + 1);
+        const size_t smem = (size_t)depth * rtk::kBlock * sizeof(int);
+        h->flagged.reserve((size_t)total * sizeof(int), st, false);          // per-pixel counts
+        h->slots.reserve((size_t)total * 3 * sizeof(float), st, false);
+        CK(cudaEventRecord(h->ev[0], st));
+        CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
+        {
+            KernelSpan ks(h, st, RTB_K_TRACE);
+            rtk::k_count_ac<<<gridFor(h, total), rtk::kBlock, smem, st>>>(h->scene, h->flagged.as<int>(), h->dFrame());
+            ks.done();
+        }
+        {
+            KernelSpan ks(h, st, RTB_K_OUTPUT);
+            rtk::k_ac_resolve<<<gridFor(h, total), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), total, h->dFrame(), h->slots.as<float>());
+            ks.done();
+        }
+        CK(cudaEventRecord(h->ev[3], st));
+        const cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        CK(cudaMemcpyAsync(fb, h->slots.p, (size_t)total * 3 * sizeof(float), kind, st));
+        if (counts) CK(cudaMemcpyAsync(counts, h->flagged.p, (size_t)total * sizeof(int), kind, st));
+        if (!onDevice) h->stats.d2hBytes += (size_t)total * (3 * sizeof(float) + (counts ? sizeof(int) : 0));
+        CK(cudaStreamSynchronize(st));
+        resolveSpans(h);
+        h->stats.primaryRays = (uint64_t)total;
+        h->stats.msTotal = elapsed(h->ev[0], h->ev[3]);
+        if (stats) *stats = h->stats;
+        return RTB_OK;
     });
 }
 

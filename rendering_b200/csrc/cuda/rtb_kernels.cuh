@@ -40,7 +40,7 @@ struct FrameCtr {
     int ssaaPixels;      // pixels flagged by k_sobel
     int overflow;        // OVF_* bits: a queue would have overflowed its capacity -> the host grows it and re-runs
     unsigned int shadowSkipped;   // shadow rays not traced because their result cannot affect the pixel
-    int pad0;
+    int acMax;           // showAC debug view: largest per-pixel box count
     unsigned long long boxTests, triTests;             // closest-hit rays (counting build)
     unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (counting build)
 };
@@ -845,6 +845,63 @@ __global__ void k_ssaa_resolve(const int* __restrict__ flagged, int flaggedCap, 
 #pragma unroll
         for (int k = 0; k < 4; ++k) c = c + loadSlot(slots, slotBase + f * 4 + k);
         storeSlot(slots, flagged[f], c / 4.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// showAC debug view (scene.cpp:607-635): boxes of the reference tree a primary ray's line passes
+// ------------------------------------------------------------------------------------------------
+// Scene::countAC / recCountAC (scene.cpp:659-669, objects.cpp:572-585) for every pixel of the frame (this view
+// renders the last row / column too, and its pixel centre is x+0.5).  counts: w*h ints.
+__global__ void __launch_bounds__(kBlock) k_count_ac(Scene sc, int* __restrict__ counts, FrameCtr* ctr)
+{
+    extern __shared__ int stackMem[];
+    int* stack = stackMem + threadIdx.x;
+    const bool useAC = sc.flags & FLAG_USE_AC;
+    const int total = sc.width * sc.height;
+    int localMax = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int y = i / sc.width, x = i - y * sc.width;
+        const RayCtx r = makeRay(sc.camPos, cameraDir(sc, (float)x, (float)y));
+        int sum = 0;
+        for (int k = 0; k < sc.nObjects; ++k) {
+            const Object& ob = sc.objects[k];
+            if (ob.type != OBJ_MESH) continue;
+            const Mesh& me = sc.meshes[ob.mesh];
+            if (me.nNodes == 0) continue;
+            int sp = 0, node = 0;
+            for (;;) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(me.nodes) + 2 * node);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(me.nodes) + 2 * node + 1);
+                if (!useAC || lineHitsBox(r, a.x, a.y, a.z, a.w, b.x, b.y)) {
+                    sum++;
+                    if (__float_as_int(b.w) < 0) {          // inner node: left child next, right child later
+                        stack[sp * kBlock] = __float_as_int(b.z);
+                        sp++;
+                        node = node + 1;
+                        continue;
+                    }
+                }
+                if (sp == 0) break;
+                sp--;
+                node = stack[sp * kBlock];
+            }
+        }
+        counts[i] = sum;
+        localMax = max(localMax, sum);
+    }
+    for (int o = 16; o > 0; o >>= 1) localMax = max(localMax, __shfl_xor_sync(0xffffffffu, localMax, o));
+    if ((threadIdx.x & 31) == 0 && localMax > 0) atomicMax(&ctr->acMax, localMax);
+}
+
+// frameBuffer = Vec3f{ (float)count / acMax }  (scene.cpp:627-632; 0/0 = NaN when no pixel sees a box, as in the reference)
+__global__ void k_ac_resolve(const int* __restrict__ counts, int total, const FrameCtr* ctr, float* __restrict__ fb)
+{
+    const int acMax = ctr->acMax;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float val = (float)counts[i];
+        val /= acMax;
+        storeSlot(fb, i, mk(val, val, val));
     }
 }
 

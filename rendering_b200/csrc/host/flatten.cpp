@@ -21,6 +21,18 @@ static RtbImage imageOf(const TextureRGB8& t, bool loaded)
 
 static void put3(float* d, const Vec3f& v) { d[0] = v.x; d[1] = v.y; d[2] = v.z; }
 
+RtbCamera flattenCamera(const Camera& camera, size_t width, size_t height)
+{
+    RtbCamera c{};
+    put3(c.pos, camera.pos);
+    const Matrix44f r = camera.rotationMatrix();
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) c.rMatrix[i * 4 + j] = r[i][j];
+    c.scale = tanf(camera.fov * 0.5f / 180.0f * (float)(3.14159265358979323846));   // scene.cpp:447
+    c.aspect = (width) / (float)height;                                              // scene.cpp:448
+    return c;
+}
+
 void flatten(const Scene& scene, FlatScene& out)
 {
     out = FlatScene{};
@@ -36,12 +48,7 @@ void flatten(const Scene& scene, FlatScene& out)
         | (options::enableSSAA ? RTB_FLAG_ENABLE_SSAA : 0u);
     out.imageName = scene.options.imageName;
 
-    put3(s.camera.pos, scene.camera.pos);
-    const Matrix44f r = scene.camera.rotationMatrix();
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) s.camera.rMatrix[i * 4 + j] = r[i][j];
-    s.camera.scale = tanf(scene.camera.fov * 0.5f / 180.0f * (float)(3.14159265358979323846));
-    s.camera.aspect = (scene.options.width) / (float)scene.options.height;
+    s.camera = flattenCamera(scene.camera, scene.options.width, scene.options.height);
 
     size_t nMeshes = 0;
     for (const auto& o : scene.objects) nMeshes += (o->objectType == ObjectType::Mesh);

@@ -28,6 +28,8 @@ struct FlatScene {
 };
 
 void flatten(const Scene& scene, FlatScene& out);
+// Camera (scene.h:51-65) -> the host-computed constants of Camera::getRay / renderWorker (scene.cpp:24-48, 447-448)
+RtbCamera flattenCamera(const Camera& camera, size_t width, size_t height);
 
 struct TreeStats { int64_t nodes, leaves, refs, maxLeaf, maxDepth, trisOutsideRoot; };
 TreeStats treeStats(const Mesh& mesh);

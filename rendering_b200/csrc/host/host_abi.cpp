@@ -97,6 +97,17 @@ int rtb_save_bmp(const char* path, const float* fb, int width, int height)
     return guarded([&]() { rtb::saveBMP(path, fb, width, height); return RTB_OK; });
 }
 
+int rtb_camera_from_angles(const float pos[3], const float rotDeg[3], float fovDeg, int width, int height, RtbCamera* out)
+{
+    if (!pos || !rotDeg || !out || width <= 0 || height <= 0) { g_lastError = "bad argument"; return RTB_ERR_ARG; }
+    Camera cam;
+    cam.pos = Vec3f{ pos[0], pos[1], pos[2] };
+    cam.rot = Vec3f{ rotDeg[0], rotDeg[1], rotDeg[2] };
+    cam.fov = fovDeg;
+    *out = rtb::flattenCamera(cam, (size_t)width, (size_t)height);
+    return RTB_OK;
+}
+
 int rtb_save_bmp_bgr8(const char* path, const uint8_t* bgr, int width, int height)
 {
     if (!path || !bgr || width <= 0 || height <= 0) { g_lastError = "bad argument"; return RTB_ERR_ARG; }

@@ -23,6 +23,7 @@ namespace {
 struct Backend {
     decltype(&rtb_create) create = nullptr;
     decltype(&rtb_render_bgr8) renderBgr8 = nullptr;
+    decltype(&rtb_render_ac) renderAc = nullptr;
     decltype(&rtb_destroy) destroy = nullptr;
     decltype(&rtb_last_error) lastError = nullptr;
 };
@@ -47,9 +48,10 @@ Backend loadBackend()
     Backend b;
     b.create = (decltype(b.create))dlsym(so, "rtb_create");
     b.renderBgr8 = (decltype(b.renderBgr8))dlsym(so, "rtb_render_bgr8");
+    b.renderAc = (decltype(b.renderAc))dlsym(so, "rtb_render_ac");
     b.destroy = (decltype(b.destroy))dlsym(so, "rtb_destroy");
     b.lastError = (decltype(b.lastError))dlsym(so, "rtb_last_error");
-    if (!b.create || !b.renderBgr8 || !b.destroy || !b.lastError)
+    if (!b.create || !b.renderBgr8 || !b.renderAc || !b.destroy || !b.lastError)
         throw rtb::Error(RTB_ERR_CUDA, "CUDA backend " + path + " lacks rtb_* symbols");
     return b;
 }
@@ -72,7 +74,6 @@ void Scene::render()
     if (!sceneLoadSuccess) return;
     const double t0 = nowMs();
     try {
-        if (options::showAC) throw rtb::Error(RTB_ERR_UNSUPPORTED, "showAC debug view is not provided by the CUDA backend");
         static Backend backend = loadBackend();
         rtb::FlatScene flat;
         rtb::flatten(*this, flat);
@@ -86,7 +87,15 @@ void Scene::render()
         // (util.cpp:46-56) run on the device, a quarter of the float framebuffer's bytes cross PCIe
         std::vector<unsigned char> pixelBytes((size_t)((options.width * 3 + 3) & ~(size_t)3) * options.height, 0);
         RtbStats stats{};
-        const int rc = backend.renderBgr8(handle, 0, (int)options.height, pixelBytes.data(), 0, nullptr, &stats);
+        int rc;
+        if (options::showAC) {
+            // debug view of the tree (scene.cpp:607-635): float frame from the backend, converted here
+            std::vector<float> frame((size_t)options.width * options.height * 3, 0.0f);
+            rc = backend.renderAc(handle, frame.data(), nullptr, 0, nullptr, &stats);
+            if (rc == RTB_OK) rtb::quantiseBGR(frame.data(), (int)options.width, (int)options.height, pixelBytes.data());
+        } else {
+            rc = backend.renderBgr8(handle, 0, (int)options.height, pixelBytes.data(), 0, nullptr, &stats);
+        }
         const std::string err = rc == RTB_OK ? "" : backend.lastError();
         backend.destroy(handle);
         if (rc != RTB_OK) throw rtb::Error(rc, err);

@@ -114,6 +114,13 @@ void saveBMP(const std::string& path, const float* fb, int width, int height)
 {
     const int pad = (4 - (width * 3) % 4) % 4;
     std::vector<unsigned char> rows((size_t)(width * 3 + pad) * height, 0);
+    quantiseBGR(fb, width, height, rows.data());
+    writeBMP(path, rows.data(), width, height);
+}
+
+void quantiseBGR(const float* fb, int width, int height, unsigned char* rows)
+{
+    const int pad = (4 - (width * 3) % 4) % 4;
     size_t o = 0;
     for (int r = height - 1; r >= 0; --r) {
         const float* src = fb + (size_t)r * width * 3;
@@ -124,7 +131,6 @@ void saveBMP(const std::string& path, const float* fb, int width, int height)
             }
         o += pad;
     }
-    writeBMP(path, rows.data(), width, height);
 }
 
 void saveBMPBytes(const std::string& path, const unsigned char* bgr, int width, int height) { writeBMP(path, bgr, width, height); }

@@ -30,6 +30,8 @@ void loadBMP(const std::string& filename, std::vector<uint8_t>& rgb, int& width,
 
 // saveImage contract (util.cpp:15-76): bottom-up rows, BGR, byte = (uint8)(clamp(v,0,1)*255).
 void saveBMP(const std::string& path, const float* fb, int width, int height);
+// the conversion alone: out holds height rows of (3*width padded to 4) bytes, bottom-up, BGR (pad bytes untouched)
+void quantiseBGR(const float* fb, int width, int height, unsigned char* out);
 // same file from already-converted pixel bytes (rtb_render_bgr8: bottom-up rows, BGR, padded to 4)
 void saveBMPBytes(const std::string& path, const unsigned char* bgr, int width, int height);
 

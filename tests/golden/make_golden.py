@@ -50,7 +50,31 @@ def resized_scene(cfg, w, h, tmpdir, name):
 ENV = dict(os.environ, MALLOC_PERTURB_="255")
 
 
+# showAC debug view: per-pixel Scene::countAC of the reference (ref_driver ac), small cases only
+AC_CASES = {"cfg2_128": ("cfg2_smooth_shading_1024", 128, 128), "cfg4_240": ("cfg4_shotgun_1080", 240, 136),
+            "cfgD_160": ("cfgD_dragon_1080", 160, 92)}
+
+
+def make_ac():
+    tmp = tempfile.mkdtemp()
+    for name, (cfg, w, h) in AC_CASES.items():
+        path = resized_scene(cfg, w, h, tmp, "ac_" + name)
+        try:
+            out = os.path.join(tmp, name + ".i32")
+            info = json.loads(subprocess.run([DRV, "ac", os.path.basename(path), out], cwd=SCENES, check=True, env=ENV,
+                                             capture_output=True, text=True).stdout.strip().splitlines()[-1])
+            counts = np.fromfile(out, np.int32).reshape(h, w)
+            assert int(counts.max()) == info["ac_max"]
+            np.savez_compressed(os.path.join(HERE, "ac_" + name + ".npz"), counts=counts)
+            print("ac", name, info, flush=True)
+        finally:
+            os.remove(path)
+
+
 def main():
+    if "--ac-only" in sys.argv:
+        return make_ac()
+    make_ac()
     out = {}
     tmp = tempfile.mkdtemp()
     for name, (cfg, w, h, store) in CASES.items():

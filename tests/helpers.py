@@ -28,6 +28,7 @@ def oracle():
         lib.rtb_oracle_render.restype = C.c_int
         lib.rtb_oracle_trace.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.rtb_oracle_cast.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_int, C.c_void_p]
+        lib.rtb_oracle_show_ac.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p]
         _oracle = lib
     return _oracle
 
@@ -76,6 +77,15 @@ def oracle_cast(scene, rays):
     rgb = np.empty((n, 3), np.float32)
     oracle().rtb_oracle_cast(scene.view, rays.ctypes.data, n, rgb.ctypes.data)
     return rgb
+
+
+def oracle_show_ac(scene):
+    """-> (float32 frame (h, w, 3), int32 counts (h, w)) of the showAC debug view"""
+    h, w = scene.height, scene.width
+    fb = np.zeros((h, w, 3), np.float32)
+    counts = np.zeros((h, w), np.int32)
+    assert oracle().rtb_oracle_show_ac(scene.view, fb.ctypes.data, counts.ctypes.data) == 0
+    return fb, counts
 
 
 def scene_text(cfg, width=None, height=None, extra_options="", replace=None):

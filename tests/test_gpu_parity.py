@@ -13,8 +13,10 @@ import pytest
 import torch
 
 import rendering_b200 as rb
-from helpers import (GOLDEN, HAVE_ASSETS, MIXED_SCENE, diff_stats, golden_case, load, needs_assets, oracle_cast,
-                     oracle_render, oracle_trace)
+import os
+
+from helpers import (GOLDEN, GOLDEN_DIR, HAVE_ASSETS, MIXED_SCENE, diff_stats, golden_case, load, needs_assets, oracle_cast,
+                     oracle_render, oracle_show_ac, oracle_trace)
 
 pytestmark = pytest.mark.gpu
 
@@ -141,6 +143,84 @@ def test_row_ranges_and_strips_reassemble_to_the_full_frame():
             assert len(part) == len(rows) == r.rows_owned(strip, rank, world)
             frame[rows] = part
         assert np.array_equal(frame.view(np.uint32), full.view(np.uint32)), (strip, world)
+
+
+@pytest.mark.parametrize("name", ["cfg2_128", "cfg4_240", "cfgD_160"])
+def test_show_ac_debug_view(name):
+    # options::showAC (scene.cpp:607-635): integer box counts must equal the reference's, the frame bit-exactly count / max
+    g, sc, _ = golden_case(name)
+    _skip_if_no_assets(g["scene"])
+    r = rb.Renderer(sc)
+    fb, counts, st = r.render_ac()
+    want = np.load(os.path.join(GOLDEN_DIR, "ac_" + name + ".npz"))["counts"]
+    assert np.array_equal(counts, want)
+    ofb, ocounts = oracle_show_ac(sc)
+    assert np.array_equal(counts, ocounts) and np.array_equal(fb.view(np.uint32), ofb.view(np.uint32))
+    # rotated camera, useAC off (every box "passes"), and a scene without meshes (0 / 0 = NaN like the reference)
+    sc2 = load(g["scene"], 96, 64, extra_options="rotation=5,20,-3\nposition=0.1,0.1,0.5")
+    a, ac, _ = rb.Renderer(sc2).render_ac()
+    b, bc = oracle_show_ac(sc2)
+    assert np.array_equal(ac, bc) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    sc3 = load(g["scene"], 64, 48, extra_options="useAC=0")
+    a, ac, _ = rb.Renderer(sc3).render_ac()
+    assert (ac == sc3.tree_stats(0)["nodes"]).all() and (a == 1.0).all()
+
+
+def test_show_ac_without_meshes_is_nan_like_the_reference():
+    a, ac, _ = rb.Renderer(rb.Scene(text=MIXED_SCENE)).render_ac()
+    assert (ac == 0).all() and np.isnan(a).all()
+
+
+def test_drop_in_cli_writes_the_reference_bmp(tmp_path):
+    # `RayTracing <scene>` -> Scene(path).render() in librtb_host.so -> dlopen librtb_cuda.so -> BMP on disk: the same
+    # CLI and side effects as the reference's main.cpp.  The file must equal the quantised oracle frame except where
+    # the 1-ulp pow() difference crosses a quantisation step, and equal this library's own pixel bytes exactly.
+    import subprocess
+    exe = os.path.join(rb.REPO_ROOT, "rendering_b200", "RayTracing")
+    for extra, name in (("", "plain"), ("showAC=1\n", "ac")):
+        text = MIXED_SCENE.replace("image_name=output/mixed", f"image_name={tmp_path}/{name}\nenableOutput=1\n{extra}".rstrip("\n"))
+        scene_file = tmp_path / f"{name}.scene"
+        scene_file.write_text(text)
+        out = subprocess.run([exe, str(scene_file)], capture_output=True, text=True, cwd=str(tmp_path))
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "Render scene" in out.stdout and "Total time" in out.stdout
+        raw = open(tmp_path / f"{name}.bmp", "rb").read()
+        sc = rb.Scene(text=text)
+        w, h = sc.width, sc.height
+        assert raw[:2] == b"BM" and len(raw) == 54 + h * w * 3
+        px = np.frombuffer(raw, np.uint8, offset=54).reshape(h, w * 3)
+        r = rb.Renderer(sc)
+        if extra:
+            fb, _, _ = r.render_ac()
+            want = (np.clip(np.nan_to_num(fb, nan=1.0), 0, 1) * np.float32(255)).astype(np.uint8)[::-1, :, ::-1].reshape(h, w * 3)
+            assert np.array_equal(px, want)
+        else:
+            mine, _ = r.render_bgr8()
+            assert np.array_equal(px, mine)
+            _, ofin, _ = oracle_render(sc)
+            oq = (np.clip(ofin, 0, 1) * np.float32(255)).astype(np.uint8)[::-1, :, ::-1].reshape(h, w * 3)
+            assert (px != oq).mean() < 1e-4
+
+
+def test_camera_sweep_on_a_resident_scene():
+    # rtb_set_camera: a persistent handle re-renders with a new camera without re-uploading the scene; the frame must be
+    # bit-identical to a fresh load of the same scene file with that camera in its [options]
+    cams = [((0.3, 0.2, 1.0), (10.0, 25.0, -5.0), 60.0), ((-0.5, 0.4, 0.5), (-8.0, -15.0, 3.0), 45.0)]
+    r = rb.Renderer(rb.Scene(text=MIXED_SCENE))
+    base, _ = r.render()
+    for pos, rot, fov in cams:
+        opts = f"position={pos[0]},{pos[1]},{pos[2]}\nrotation={rot[0]},{rot[1]},{rot[2]}\nfov={fov}"
+        sc = rb.Scene(text=MIXED_SCENE.replace("[options]\n", "[options]\n" + opts + "\n"))
+        fresh, _ = rb.Renderer(sc).render()
+        r.set_camera(pos, rot, fov)
+        moved, _ = r.render()
+        assert np.array_equal(moved.view(np.uint32), fresh.view(np.uint32))
+        assert not np.array_equal(moved.view(np.uint32), base.view(np.uint32))
+        _, ofin, _ = oracle_render(sc)
+        assert diff_stats(moved, ofin)["rms"] <= RMS_TOL
+    r.set_camera()
+    again, _ = r.render()
+    assert np.array_equal(again.view(np.uint32), base.view(np.uint32))
 
 
 def test_strips_written_in_place_assemble_the_frame():

@@ -148,3 +148,14 @@ def test_bmp_from_pixel_bytes_equals_bmp_from_floats(tmp_path):
         body[:, : w * 3] = (np.clip(fb, 0, 1) * np.float32(255)).astype(np.uint8)[::-1, :, ::-1].reshape(h, w * 3)
         save_bmp_bgr8(b, body, w, h)
         assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def test_camera_from_angles_equals_the_loaders_camera():
+    import ctypes as C
+    from rendering_b200 import _ffi
+    text = "[options]\nwidth=96\nheight=64\nfov=47\nposition=0.3,-0.2,1.5\nrotation=10,25,-5\n[end]\n"
+    want = rb.Scene(text=text).desc.camera
+    got = _ffi.RtbCamera()
+    rc = _ffi.host_lib().rtb_camera_from_angles((C.c_float * 3)(0.3, -0.2, 1.5), (C.c_float * 3)(10, 25, -5), 47.0, 96, 64, C.byref(got))
+    assert rc == 0
+    assert bytes(want) == bytes(got)

@@ -5,7 +5,9 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, HAVE_ASSETS, diff_stats, golden_case, needs_assets, oracle_render, shim_render
+import os
+
+from helpers import GOLDEN, GOLDEN_DIR, HAVE_ASSETS, diff_stats, golden_case, needs_assets, oracle_render, oracle_show_ac, shim_render
 
 SMALL = ["cfg1_256", "cfg2_128", "cfg3_240", "cfg4_240", "cfgD_160"]
 
@@ -60,3 +62,15 @@ def test_device_arithmetic_on_cpu_matches_oracle(name):
             assert d["pixels_differing"] == 0
         else:
             assert d["pixels_differing"] <= 0.001 * a.shape[0] * a.shape[1] and d["max_abs"] <= 2.5e-7
+
+
+@pytest.mark.parametrize("name", ["cfg2_128", "cfg4_240", "cfgD_160"])
+def test_oracle_show_ac_matches_reference_counts(name):
+    """showAC debug view (scene.cpp:607-635): per-pixel Scene::countAC of the unmodified reference (tests/golden/ac_*.npz)."""
+    _skip_if_no_assets(name)
+    g, sc, _ = golden_case(name)
+    want = np.load(os.path.join(GOLDEN_DIR, "ac_" + name + ".npz"))["counts"]
+    fb, counts = oracle_show_ac(sc)
+    assert np.array_equal(counts, want)
+    expect = (want.astype(np.float32) / np.float32(want.max()))
+    assert np.array_equal(fb[..., 0], expect) and np.array_equal(fb[..., 1], expect) and np.array_equal(fb[..., 2], expect)
