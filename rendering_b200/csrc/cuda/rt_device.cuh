@@ -363,14 +363,18 @@ RT_HD Surface surfaceAt(const Scene& sc, const Object& ob, V3 orig, V3 dir, floa
         tex.x = tc[2] * u + tc[4] * v + tc[0] * w;
         tex.y = tc[3] * u + tc[5] * v + tc[1] * w;
         const V3 nb = mk(n[3], n[4], n[5]), nc = mk(n[6], n[7], n[8]), na = mk(n[0], n[1], n[2]);
+        // issue the (up to three) independent texel fetches before the dependent FP64 normalisations
+        const bool shade = !(sc.flags & FLAG_SHOW_NORMALS);
+        const bool wantN = me.normal.w > 0, wantD = shade && me.diffuse.w > 0, wantS = shade && ob.material == MAT_PHONG && me.specular.w > 0;
+        float nr = 0, ng = 0, nbl = 0, dr = 0, dg = 0, db = 0, sr = 0, sg = 0, sb = 0;
+        if (wantN) fetchTexel(me.normal, texIndex(me.normal.w, tex.x), texIndex(me.normal.h, tex.y), nr, ng, nbl);
+        if (wantD) fetchTexel(me.diffuse, texIndex(me.diffuse.w, tex.x), texIndex(me.diffuse.h, tex.y), dr, dg, db);
+        if (wantS) fetchTexel(me.specular, texIndex(me.specular.w, tex.x), texIndex(me.specular.h, tex.y), sr, sg, sb);
         s.N = normalize((nb * u + nc * v + na * w) / 3.0f);
-        if (me.normal.w > 0) {
+        if (wantN) {
             const float* tb = me.tan + (size_t)tri * 6;
-            const int ix = texIndex(me.normal.w, tex.x), iy = texIndex(me.normal.h, tex.y);
-            float r, g, b;
-            fetchTexel(me.normal, ix, iy, r, g, b);
             // load-time conversion (objects.cpp:431-433) then the lookup's own normalize (:148)
-            V3 tn = normalize(mk(r * 2 - 1, -(g * 2 - 1), b));
+            V3 tn = normalize(mk(nr * 2 - 1, -(ng * 2 - 1), nbl));
             tn = normalize(tn);
             // rows tangent, bitangent, N; fourth row and column zero (objects.cpp:133-139)
             V3 d;
@@ -381,18 +385,8 @@ RT_HD Surface surfaceAt(const Scene& sc, const Object& ob, V3 orig, V3 dir, floa
             if (wq != 0.0f && wq != 1.0f) { const float wi = 1.0f / wq; d.x *= wi; d.y *= wi; d.z *= wi; }
             s.N = normalize(d);
         }
-        if (!(sc.flags & FLAG_SHOW_NORMALS)) {
-            if (me.diffuse.w > 0) {
-                const int ix = texIndex(me.diffuse.w, tex.x), iy = texIndex(me.diffuse.h, tex.y);
-                fetchTexel(me.diffuse, ix, iy, s.color.x, s.color.y, s.color.z);
-            }
-            if (ob.material == MAT_PHONG && me.specular.w > 0) {
-                const int ix = texIndex(me.specular.w, tex.x), iy = texIndex(me.specular.h, tex.y);
-                float r, g, b;
-                fetchTexel(me.specular, ix, iy, r, g, b);
-                s.specCoef = (r + g + b) / 3.0f;   // objects.cpp:455
-            }
-        }
+        if (wantD) s.color = mk(dr, dg, db);
+        if (wantS) s.specCoef = (sr + sg + sb) / 3.0f;   // objects.cpp:455
     }
     return s;
 }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cfloat>
@@ -86,6 +87,11 @@ struct RtbHandle {
     std::vector<TextureRes> textures;
     bool kernelTiming = false;         // bracket every launch with CUDA events (RTB_CREATE_KERNEL_TIMING -> RtbStats.msKernel)
     std::vector<int> refTreeDepth;     // depth of every mesh's reference tree (showAC walk)
+    // world-space boxes (lo.xyz, hi.xyz) around everything a primary ray can hit, for the screen-space bounds of the
+    // geometry; `unbounded` when a plane is present or misses need their direction (skybox)
+    std::vector<std::array<float, 6>> geomBounds;
+    bool unbounded = false;
+    int primRect[4] = { 0, 0, 0, 0 };  // pixel columns [x0,x1) and rows [y0,y1) primary rays are generated for
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
     int walkBlocksPerSm[4] = { 1, 1, 1, 1 };   // resident CTAs per SM of k_walk<false, GEN 0..2> / k_walk<true> with that stack
@@ -143,12 +149,24 @@ T* upload(RtbHandle* h, const T* src, size_t n)
 rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
 {
     rt::Image out{};
-    const std::vector<unsigned char> rgba = rtpack::packRGBA(im);
-    if (rgba.empty()) return out;
+    if (!im.rgb || im.width <= 0 || im.height <= 0) return out;
+    const size_t nTexels = (size_t)im.width * im.height;
+    // 3 B / texel over PCIe, widened to RGBA8 on the device, then laid out as a CUDA array (2D-local texture fetches)
+    unsigned char* dRgb = nullptr;
+    uchar4* dRgba = nullptr;
+    CK(cudaMalloc((void**)&dRgb, nTexels * 3));
+    CK(cudaMalloc((void**)&dRgba, nTexels * sizeof(uchar4)));
+    CK(cudaMemcpy(dRgb, im.rgb, nTexels * 3, cudaMemcpyHostToDevice));
+    const int blocks = (int)std::min<size_t>((nTexels + 255) / 256, (size_t)h->smCount * 16);
+    rtk::k_rgb_to_rgba<<<blocks, 256>>>(dRgb, nTexels, dRgba);
+    CK(cudaGetLastError());
     TextureRes res;
     const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
     CK(cudaMallocArray(&res.array, &fmt, im.width, im.height));
-    CK(cudaMemcpy2DToArray(res.array, 0, 0, rgba.data(), (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2DToArray(res.array, 0, 0, dRgba, (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyDeviceToDevice));
+    CK(cudaDeviceSynchronize());
+    CK(cudaFree(dRgb));
+    CK(cudaFree(dRgba));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = res.array;
@@ -178,7 +196,52 @@ int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
     d.triRefOff = upload(h, fp.triRefOff.data(), fp.triRefOff.size());
     d.triRefs = upload(h, fp.triRefs.data(), fp.triRefs.size());
     d.parent = upload(h, fp.parent.data(), fp.parent.size());
+    if (!fp.nodes.empty() && m.nTris > 0) {
+        const rtbvh::Node& root = fp.nodes[0];
+        std::array<float, 6> b;
+        for (int a = 0; a < 3; ++a) {
+            b[a] = std::min(root.c0lo[a], root.c1lo[a]);          // an empty child has lo = +FLT_MAX, hi = -FLT_MAX
+            b[3 + a] = std::max(root.c0hi[a], root.c1hi[a]);
+        }
+        h->geomBounds.push_back(b);
+    }
     return fp.maxDepth;
+}
+
+// Pixel rectangle that contains the projection of every bounded object, expanded by 2 pixels (the projection uses
+// the camera constants in double; rounding is ~1e-4 pixel).  The whole rendered frame when anything is unbounded,
+// behind / around the camera, or when missing rays need their direction.
+void computePrimaryRect(RtbHandle* h)
+{
+    const rt::Scene& sc = h->scene;
+    const int wm1 = sc.width - 1, hm1 = sc.height - 1;
+    int* r = h->primRect;
+    r[0] = 0; r[1] = wm1; r[2] = 0; r[3] = hm1;
+    if (h->unbounded || (sc.flags & rt::FLAG_SKYBOX)) return;
+    double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
+    for (const auto& b : h->geomBounds) {
+        for (int c = 0; c < 8; ++c) {
+            const double v[3] = { (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, (double)b[(c & 4) ? 5 : 2] - sc.camPos.z };
+            if (!(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]))) return;
+            // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
+            double cam[3];
+            for (int i = 0; i < 3; ++i) cam[i] = v[0] * sc.camM[i * 4 + 0] + v[1] * sc.camM[i * 4 + 1] + v[2] * sc.camM[i * 4 + 2];
+            const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            if (!(cam[2] < -1e-4 * len)) return;                   // at or behind the camera plane: no bound
+            const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
+            // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
+            const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
+            const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
+            if (!(std::isfinite(px) && std::isfinite(py))) return;
+            minX = std::min(minX, px); maxX = std::max(maxX, px);
+            minY = std::min(minY, py); maxY = std::max(maxY, py);
+        }
+    }
+    if (h->geomBounds.empty()) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+    auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
+    r[0] = clampi(std::floor(minX) - 2, 0, wm1); r[1] = clampi(std::ceil(maxX) + 3, 0, wm1);
+    r[2] = clampi(std::floor(minY) - 2, 0, hm1); r[3] = clampi(std::ceil(maxY) + 3, 0, hm1);
+    if (r[1] <= r[0] || r[3] <= r[2]) r[0] = r[1] = r[2] = r[3] = 0;
 }
 
 size_t stackBytes(const RtbHandle* h) { return (size_t)h->stackEntries * rtk::kBlock * sizeof(int); }
@@ -416,11 +479,20 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                 if (y + dy >= 0 && y + dy < ht - 1) need[y + dy] = 1;
         for (int y = 0; y < ht; ++y) if (need[y]) p1rows.push_back(y);
     }
-    uploadRows(h, st, h->rowsA, h->rowsAHost, p1rows);
+    // primary rays are generated only inside the screen-space bounds of the geometry (computePrimaryRect); the pixels
+    // outside are misses by construction and receive the background colour from k_fill_background
+    const bool literalWalk = h->createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK);
+    const int* rect = h->primRect;
+    const bool culled = !literalWalk && (rect[0] > 0 || rect[1] < w - 1 || rect[2] > 0 || rect[3] < ht - 1);
+    std::vector<int> genRows;
+    if (culled) { for (int y : p1rows) if (y >= rect[2] && y < rect[3]) genRows.push_back(y); }
+    else genRows = p1rows;
+    const int genX0 = culled ? rect[0] : 0, genCols = culled ? rect[1] - rect[0] : w - 1;
+    uploadRows(h, st, h->rowsA, h->rowsAHost, genRows);
     uploadRows(h, st, h->rowsB, h->rowsBHost, owned);
 
     const long long nPixels = (long long)p1rows.size() * (w - 1);
-    const long long n0 = nPixels > 0 ? rtk::raygenPaddedCount(w, (int)p1rows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
+    const long long n0 = (!genRows.empty() && genCols > 0) ? rtk::raygenPaddedCount(genCols + 1, (int)genRows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
     const long long interiorPixels = ssaa ? (long long)owned.size() * w : 0;
     // SSAA capacity: what the last frame flagged plus head-room, at least 1/16 of the owned pixels; a frame that
     // flags more sets OVF_FLAGGED and is re-run with the exact count
@@ -435,17 +507,22 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
         const int sampleBase = (int)framePixels;
 
         CK(cudaEventRecord(h->ev[0], st));
-        CK(cudaMemsetAsync(h->slots.p, 0, (size_t)framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
+        if (culled) {
+            KernelSpan ks(h, st, RTB_K_RAYGEN);
+            rtk::k_fill_background<<<gridFor(h, framePixels), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, ht, sc.background);
+            ks.done();
+        } else {
+            CK(cudaMemsetAsync(h->slots.p, 0, (size_t)framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
+        }
         CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
-        const bool literalWalk = h->createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK);
         if (n0 > 0) {
             if (literalWalk) {   // the literal reference walk reads a materialised queue
                 KernelSpan ks(h, st, RTB_K_RAYGEN);
-                rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)p1rows.size(), h->rays[0].view(), h->dLevel(0, 0));
+                rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)genRows.size(), h->rays[0].view(), h->dLevel(0, 0));
                 ks.done();
                 enqueueLevels(h, st, 0, framePixels);
             } else {
-                enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)p1rows.size(), 0, h->slots.as<float>(), h->sceneDev });
+                enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)genRows.size(), 0, genX0, genCols, h->slots.as<float>(), h->sceneDev });
             }
         }
         CK(cudaEventRecord(h->ev[1], st));
@@ -494,7 +571,7 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                 ks.done();
                 enqueueLevels(h, st, 1, framePixels);
             } else {
-                enqueueLevels(h, st, 1, framePixels, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, sampleBase, h->slots.as<float>(), h->sceneDev });
+                enqueueLevels(h, st, 1, framePixels, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, sampleBase, 0, 0, h->slots.as<float>(), h->sceneDev });
             }
             KernelSpan ks(h, st, RTB_K_OUTPUT);
             rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
@@ -662,6 +739,16 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             meshes.push_back(d);
         }
         h->sceneDev = upload(h, &h->scene, 1);
+        for (int i = 0; i < s->nObjects; ++i) {
+            const RtbObject& o = s->objects[i];
+            if (o.type == RTB_OBJ_PLANE) h->unbounded = true;
+            else if (o.type == RTB_OBJ_SPHERE) {
+                const float rad = std::sqrt(std::max(0.0f, o.r2)) * 1.001f + 1e-6f;
+                if (!(rad < FLT_MAX)) h->unbounded = true;
+                h->geomBounds.push_back({ o.pos[0] - rad, o.pos[1] - rad, o.pos[2] - rad, o.pos[0] + rad, o.pos[1] + rad, o.pos[2] + rad });
+            }
+        }
+        computePrimaryRect(h);
         // recursion levels: only Reflective / Transparent hits spawn children (scene.cpp:854-941)
         bool spawns = false;
         for (int i = 0; i < s->nObjects; ++i)
@@ -701,6 +788,7 @@ int rtb_set_camera(RtbHandle* h, const RtbCamera* camera)
         h->scene.camAspect = camera->aspect;
         CK(cudaStreamSynchronize(h->ownStream));
         CK(cudaMemcpy(h->sceneDev, &h->scene, sizeof(rt::Scene), cudaMemcpyHostToDevice));
+        computePrimaryRect(h);
         return RTB_OK;
     });
 }

@@ -393,6 +393,8 @@ struct GenArgs {
     const int* list;     // GEN_PRIMARY: image rows to render; GEN_SSAA: flagged pixels
     int count;           // GEN_PRIMARY: number of rows; GEN_SSAA: capacity of the flagged list
     int slotBase;        // GEN_SSAA: first sample slot
+    int x0, cols;        // GEN_PRIMARY: pixel columns [x0, x0 + cols) to generate rays for (the screen-space bounds of the
+                         // geometry; pixels outside were pre-filled with the background colour by k_fill_background)
     float* slots;        // colour slots (misses of generated rays are resolved here)
     const Scene* scene;  // device-resident copy of the scene header for the out-of-line helpers below
 };
@@ -418,11 +420,11 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
     const int nSurf = nSurfRaw > 0 ? nSurfRaw : 1;
     long long total;
     if (ANY) total = (long long)nSurfRaw * S;
-    else if (GEN == GEN_PRIMARY) total = raygenPaddedCount(sc.width, gen.count);
+    else if (GEN == GEN_PRIMARY) total = raygenPaddedCount(gen.cols + 1, gen.count);
     else if (GEN == GEN_SSAA) total = 4LL * min(ctr->ssaaPixels, gen.count);
     else total = min(lv->nRays, cap);
     if (!ANY && GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
-    const int wm1 = sc.width - 1, tilesX = (wm1 + 7) / 8;
+    const int tilesX = (gen.cols + 7) / 8;
 
     bool have = false, exhausted = false;
     long long out = 0;                 // where the result goes: ray index (closest) or visibility index (ANY)
@@ -458,9 +460,10 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
                     V3 o, d;
                     if (GEN == GEN_PRIMARY) {
                         const long long tile = my >> 5;
-                        const int x = (int)(tile % tilesX) * 8 + ((int)my & 7);
+                        const int xr = (int)(tile % tilesX) * 8 + ((int)my & 7);
+                        const int x = gen.x0 + xr;
                         const int rr = (int)(tile / tilesX) * 4 + (((int)my >> 3) & 3);
-                        live = x < wm1 && rr < gen.count;
+                        live = xr < gen.cols && rr < gen.count;
                         if (live) {
                             const int y = __ldg(gen.list + rr);
                             o = sc.camPos;
@@ -617,7 +620,10 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
 // ------------------------------------------------------------------------------------------------
 // shade stage: the four material branches of castRay (scene.cpp:780-941)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_shade(Scene sc, RayQueue q, SurfQueue surf, const unsigned char* __restrict__ vis,
+#ifndef RTB_SHADE_MIN_BLOCKS
+#define RTB_SHADE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kBlock, RTB_SHADE_MIN_BLOCKS) k_shade(Scene sc, RayQueue q, SurfQueue surf, const unsigned char* __restrict__ vis,
     int depth, RayQueue next, int nextCap, Interior* __restrict__ interiors, int interiorCap,
     float* __restrict__ slots, int slotBase, int slotCap, FrameCtr* ctr, LevelCtr* lv)
 {
@@ -781,36 +787,76 @@ __global__ void k_combine(const Interior* __restrict__ interiors, const LevelCtr
 // rows[]: image rows owned by this call; only interior pixels get a flag (scene.cpp:554-555).  Pixels are
 // visited in the 8x4 tiles of ray generation (one warp = one tile), so the compacted list keeps
 // neighbouring pixels — and with them the 4 samples of each — next to each other in the SSAA ray queue.
-__global__ void k_sobel(int width, int height, const float* __restrict__ fb, const int* __restrict__ rows, int nRows,
+__global__ void __launch_bounds__(kBlock) k_sobel(int width, int height, const float* __restrict__ fb, const int* __restrict__ rows, int nRows,
     int* __restrict__ flagged, int flaggedCap, FrameCtr* ctr)
 {
+    // one warp = one 8x4 pixel tile; its 10x6 pixel neighbourhood (180 floats per channel row) is staged in shared
+    // memory with coalesced row loads when the tile's four rows are consecutive image rows (always, unless a strip
+    // partition cuts through the tile); otherwise every lane reads its 3x3 window directly
+    __shared__ float tileMem[kBlock / 32][6][32];
+    float (*tile)[32] = tileMem[threadIdx.x >> 5];
     const int tilesX = (width + 7) / 8;
     const long long total = (long long)tilesX * ((nRows + 3) / 4) * 32;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         bool flag = false;
         int pix = 0;
-        const long long tile = i >> 5;
+        const long long tileIdx = i >> 5;
         const int lane = (int)(i & 31);
-        const int x = (int)(tile % tilesX) * 8 + (lane & 7);
-        const int r = (int)(tile / tilesX) * 4 + (lane >> 3);
-        if (x < width && r < nRows) {
-            const int y = rows[r];
-            if (y >= 1 && y < height - 1 && x >= 1 && x < width - 1) {
-                V3 gx = mk(0.0f, 0.0f, 0.0f), gy = mk(0.0f, 0.0f, 0.0f);
-                const float op[3][3] = { { -1, 0, 1 }, { -2, 0, 2 }, { -1, 0, 1 } };
+        const int x0 = (int)(tileIdx % tilesX) * 8, r0 = (int)(tileIdx / tilesX) * 4;
+        const int x = x0 + (lane & 7), r = r0 + (lane >> 3);
+        const int yFirst = rows[r0], rLast = min(r0 + 3, nRows - 1);
+        const bool staged = rows[rLast] - yFirst == rLast - r0 && yFirst >= 1 && yFirst + (rLast - r0) < height - 1;
+        const bool inside = x < width && r < nRows;
+        const int y = inside ? rows[r] : 0;
+        const bool interior = inside && y >= 1 && y < height - 1 && x >= 1 && x < width - 1;
+        V3 gx = mk(0.0f, 0.0f, 0.0f), gy = mk(0.0f, 0.0f, 0.0f);
+        const float op[3][3] = { { -1, 0, 1 }, { -2, 0, 2 }, { -1, 0, 1 } };
+        if (staged) {
+            // rows yFirst-1 .. yFirst+4, columns x0-1 .. x0+8: 30 floats per row, lanes 0..29 load one each
+            const int cBase = (x0 - 1) * 3;
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+                const int yy = yFirst - 1 + rr;
+                const int c = cBase + lane;
+                float v = 0.0f;
+                if (lane < 30 && yy < height && c >= 0 && c < width * 3) v = fb[(size_t)yy * width * 3 + c];
+                tile[rr][lane] = v;
+            }
+            __syncwarp();
+            if (interior) {
+                const int ly = y - yFirst, lx = (lane & 7) * 3;   // window rows ly..ly+2, float columns lx..lx+8
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
-                        const V3 c = loadSlot(fb, (y - 1 + a) * width + x - 1 + b);
+                        const V3 c = mk(tile[ly + a][lx + 3 * b], tile[ly + a][lx + 3 * b + 1], tile[ly + a][lx + 3 * b + 2]);
                         gx = gx + c * op[a][b];
                         gy = gy + c * op[b][a];
                     }
-                const float lx = length(gx), ly = length(gy);
-                // powf(v, 2) of the reference is v*v to within glibc's rounding (scene.cpp:565)
-                flag = sqrtf(lx * lx + ly * ly) > 0.5f;
-                pix = y * width + x;
             }
+        } else if (interior) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    const V3 c = loadSlot(fb, (y - 1 + a) * width + x - 1 + b);
+                    gx = gx + c * op[a][b];
+                    gy = gy + c * op[b][a];
+                }
+        }
+        if (interior) {
+            // val = sqrtf(powf(|Gx|,2) + powf(|Gy|,2)) > 0.5f with |G| = (float)sqrt((double)G.G)  (scene.cpp:565-566,
+            // geometry.h:99).  Away from the threshold the float sum of squares decides with a wide margin and the
+            // double-precision square roots are skipped; powf(v, 2) is v*v to within glibc's rounding.
+            const float s2 = dot(gx, gx) + dot(gy, gy);
+            if (s2 > 0.2501f) flag = true;
+            else if (s2 < 0.2499f) flag = false;
+            else {
+                const float lx = length(gx), ly = length(gy);
+                flag = sqrtf(lx * lx + ly * ly) > 0.5f;
+            }
+            pix = y * width + x;
         }
         const int f = warpAlloc(&ctr->ssaaPixels, flag, 1);
         if (flag) {
@@ -846,6 +892,33 @@ __global__ void k_ssaa_resolve(const int* __restrict__ flagged, int flaggedCap, 
         for (int k = 0; k < 4; ++k) c = c + loadSlot(slots, slotBase + f * 4 + k);
         storeSlot(slots, flagged[f], c / 4.0f);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// background fill
+// ------------------------------------------------------------------------------------------------
+// When the geometry's screen-space bounds cover only part of the frame, primary rays are generated for that part
+// only; every other rendered pixel is what castRay returns for a miss without a skybox: the background colour
+// (scene.cpp:383,945).  The last row and column stay black (never rendered, scene.cpp:369-372).
+__global__ void k_fill_background(float* __restrict__ fb, int width, int height, V3 bg)
+{
+    const long long total = (long long)width * height;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+        const bool rendered = x < width - 1 && y < height - 1;
+        storeSlot(fb, (int)i, rendered ? bg : mk(0.0f, 0.0f, 0.0f));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// texture upload: loadBMP's 3-byte texels (util.cpp:78-113) -> RGBA8 on the device
+// ------------------------------------------------------------------------------------------------
+// The reference expands every map to float on the host (12 B / texel, objects.cpp:396-458); here the file's bytes go
+// over PCIe as they are (3 B / texel) and are widened to the 4 B / texel a texture object needs by this kernel.
+__global__ void k_rgb_to_rgba(const unsigned char* __restrict__ rgb, size_t nTexels, uchar4* __restrict__ rgba)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nTexels; i += (size_t)gridDim.x * blockDim.x)
+        rgba[i] = make_uchar4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 255);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -79,6 +79,28 @@ def test_full_size_configs_vs_oracle(cfg, exact):
     assert not fb[-1].any() and not fb[:, -1].any()
 
 
+def test_cfg5_4k_frame_vs_oracle_and_partition_properties():
+    # BASELINE config 5: shotgun.scene at 3840x2160.  Against the oracle at full size, plus two size-independent
+    # properties: strips of any partition reassemble to the same bits, and a second frame on the handle is identical.
+    _skip_if_no_assets("cfg5")
+    sc = rb.Scene(rb.scene_path("cfg5_shotgun_2160"))
+    r = rb.Renderer(sc)
+    fb, st = r.render()
+    _, ofin, ocnt = oracle_render(sc)
+    assert st["rays"] == ocnt["rays"] and st["ssaaPixels"] == ocnt["ssaaPixels"]
+    d = diff_stats(fb, ofin)
+    assert d["rms"] <= RMS_TOL and d["max_abs"] <= 2.5e-7 and d["pixels_differing"] <= 1e-3 * fb.shape[0] * fb.shape[1], d
+    assert not fb[-1].any() and not fb[:, -1].any()
+    from rendering_b200 import dist as rdist
+    frame = np.zeros_like(fb)
+    for rank in range(8):
+        part, _ = r.render_strips(8, rank, 8)
+        frame[rdist.owned_rows(sc.height, 8, rank, 8)] = part
+    assert np.array_equal(frame.view(np.uint32), fb.view(np.uint32))
+    again, _ = r.render()
+    assert np.array_equal(again.view(np.uint32), fb.view(np.uint32))
+
+
 def test_default_handle_equals_counting_handle():
     sc = rb.Scene(text=MIXED_SCENE)
     a = rb.Renderer(sc, counters=True)
@@ -169,6 +191,51 @@ def test_show_ac_debug_view(name):
 def test_show_ac_without_meshes_is_nan_like_the_reference():
     a, ac, _ = rb.Renderer(rb.Scene(text=MIXED_SCENE)).render_ac()
     assert (ac == 0).all() and np.isnan(a).all()
+
+
+BOUNDED_SCENE = """
+[options]
+width=160
+height=120
+background_color=0.25,0.5,0.75
+{camera}
+[light]
+type=point
+position=-1,3,1
+intensity=0.8
+[light]
+type=distant
+direction=0.2,-1,-0.4
+intensity=0.4
+[object]
+type=sphere
+pos=-0.8,0.2,-4
+radius=0.7
+color=0.9,0.3,0.2
+[object]
+type=sphere
+pos=1.1,-0.3,-5
+radius=1.1
+color=0.2,0.8,0.4
+[end]
+"""
+
+
+@pytest.mark.parametrize("camera", [
+    "", "position=0.5,0.2,1\nrotation=4,-12,3", "fov=25", "fov=120",
+    "rotation=0,35,0",              # objects partly outside the frame
+    "rotation=0,170,0",             # objects behind the camera: no bound, nothing visible
+    "position=1.1,-0.3,-5",         # camera inside a sphere
+    "position=-0.8,0.2,-3.2",       # camera just outside a sphere (bounds straddle the camera plane)
+])
+def test_primary_rays_limited_to_the_geometry_bounds_stay_exact(camera):
+    # without a plane or skybox, primary rays are generated only inside the projected bounds of the objects and the rest
+    # of the frame is pre-filled with the background colour: must be indistinguishable from tracing every pixel
+    sc = rb.Scene(text=BOUNDED_SCENE.format(camera=camera))
+    check_against_oracle(sc, exact=True)
+    if HAVE_ASSETS and camera in ("", "rotation=0,35,0"):
+        sc = load("cfgD_dragon_1080", 200, 120, extra_options=camera or "position=0.4,0.1,0.3")
+        check_against_oracle(sc, exact=True, counters=False)
 
 
 def test_drop_in_cli_writes_the_reference_bmp(tmp_path):
