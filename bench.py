@@ -106,7 +106,13 @@ def reference_arm(args):
     if rank != 0:
         return
     rays = golden_rays(args.scene)
-    ms, info = run_reference(args.scene, args.steps, max(1, args.warmup), rays)
+    # bounded: a frame of the 250k-triangle scene takes the reference tens of seconds; cap the run at a few minutes
+    probe, info = run_reference(args.scene, 1, 0, rays)
+    budget_frames = int(max(1, min(args.steps, 120000.0 / max(probe[0], 1e-3))))
+    if budget_frames > 1 or args.warmup > 0 and probe[0] < 30000.0:
+        ms, info = run_reference(args.scene, budget_frames, 1 if probe[0] < 30000.0 else 0, rays)
+    else:
+        ms = probe
     rays = info.pop("rays")
     mean_ms = sum(ms) / len(ms)
     value = rays / (mean_ms * 1e-3) / 1e6
@@ -355,7 +361,14 @@ def ours(args):
     }
     if args.gpus == 1 and not args.no_cpu_baseline:
         try:
-            ms, info = run_reference(args.scene, 8, 1, rays)
+            # bounded sample: one probe frame tells how many full frames fit in ~20 s of CPU time
+            probe, info = run_reference(args.scene, 1, 0, rays)
+            frames = int(max(1, min(8, 20000.0 / max(probe[0], 1e-3))))
+            if frames > 1:
+                ms, info = run_reference(args.scene, frames, 1, rays)
+            else:
+                ms = probe
+                info["sample"] = info["sample"].replace("after 0 warm-up frame(s)", "single frame, no warm-up (one frame takes %.0f s)" % (probe[0] / 1e3))
             info.pop("rays", None)
             mean_ms = sum(ms) / len(ms)
             line["cpu_baseline"] = dict(info, value=rays / (mean_ms * 1e-3) / 1e6, unit="Mrays/s", ms_per_frame=mean_ms)

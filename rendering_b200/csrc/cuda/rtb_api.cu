@@ -738,7 +738,6 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             if (m.nNodes > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
             meshes.push_back(d);
         }
-        h->sceneDev = upload(h, &h->scene, 1);
         for (int i = 0; i < s->nObjects; ++i) {
             const RtbObject& o = s->objects[i];
             if (o.type == RTB_OBJ_PLANE) h->unbounded = true;
@@ -770,6 +769,8 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         h->scene.areaPoints = upload(h, s->areaPoints, (size_t)s->nAreaPoints * 3);
         if (s->flags & RTB_FLAG_USE_SKYBOX)
             for (int k = 0; k < 6; ++k) h->scene.sky[k] = uploadImage(h, s->skybox[k]);
+        // the header's resident copy (out-of-line device helpers read it): only now are all of its pointers final
+        h->sceneDev = upload(h, &h->scene, 1);
         return RTB_OK;
     });
     if (rc != RTB_OK) { destroyHandle(h); return rc; }

@@ -29,22 +29,30 @@ def _skip_if_no_assets(cfg):
 
 
 def check_against_oracle(sc, exact, counters=True):
-    r = rb.Renderer(sc, counters=counters)
-    fb, p1, st = r.render(want_pass1=True)
-    r.close()
+    """Renders with the default (fast-path) handle and, when `counters`, also with the literal-walk counting handle;
+    both must match the oracle, each other bit for bit, and the reference's work counters."""
     o1, ofin, ocnt = oracle_render(sc)
-    assert st["rays"] == ocnt["rays"]
-    assert st["ssaaPixels"] == ocnt["ssaaPixels"]
-    if counters:
-        assert st["boxTests"] == ocnt["boxTests"] and st["triTests"] == ocnt["triTests"]
-    for a, b in ((p1, o1), (fb, ofin)):
-        d = diff_stats(a, b)
-        if exact:
-            assert d["pixels_differing"] == 0, d
-        else:
-            assert d["rms"] <= RMS_TOL, d
-            assert d["max_abs"] <= 2.5e-7 and d["pixels_differing"] <= 1e-3 * a.shape[0] * a.shape[1], d
-    return fb, p1, st
+    results = []
+    for counting in ([False, True] if counters else [False]):
+        r = rb.Renderer(sc, counters=counting)
+        fb, p1, st = r.render(want_pass1=True)
+        r.close()
+        assert st["rays"] == ocnt["rays"]
+        assert st["ssaaPixels"] == ocnt["ssaaPixels"]
+        if counting:
+            assert st["boxTests"] == ocnt["boxTests"] and st["triTests"] == ocnt["triTests"]
+        for a, b in ((p1, o1), (fb, ofin)):
+            d = diff_stats(a, b)
+            if exact:
+                assert d["pixels_differing"] == 0, d
+            else:
+                assert d["rms"] <= RMS_TOL, d
+                assert d["max_abs"] <= 2.5e-7 and d["pixels_differing"] <= 1e-3 * a.shape[0] * a.shape[1], d
+        results.append((fb, p1, st))
+    if len(results) == 2:
+        assert np.array_equal(results[0][0].view(np.uint32), results[1][0].view(np.uint32))
+        assert np.array_equal(results[0][1].view(np.uint32), results[1][1].view(np.uint32))
+    return results[-1]
 
 
 @pytest.mark.parametrize("name", ["cfg1_256", "cfg2_128", "cfg3_240", "cfg4_240", "cfgD_160"])
