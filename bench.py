@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default=DEFAULT_SCENE)
-    ap.add_argument("--strip-rows", type=int, default=8)
+    ap.add_argument("--strip-rows", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1: how the strips reach rank 0 (p2p = NVLink stores into rank 0's symmetric-memory frame)")

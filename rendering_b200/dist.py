@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-DEFAULT_STRIP_ROWS = 8
+DEFAULT_STRIP_ROWS = 16
 
 
 def owned_rows(height: int, strip_rows: int, rank: int, world: int) -> np.ndarray:
