@@ -384,9 +384,10 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQue
 // only hits are written to the queue for the surface and shade stages.
 constexpr int kDone = (int)0x80000000;   // cursor value: no mesh traversal in progress
 #ifndef RTB_REFILL_BELOW
-#define RTB_REFILL_BELOW 10
+#define RTB_REFILL_BELOW 1
 #endif
 constexpr int kRefillBelow = RTB_REFILL_BELOW;
+
 enum { GEN_QUEUE = 0, GEN_PRIMARY = 1, GEN_SSAA = 2 };
 
 struct GenArgs {
@@ -442,9 +443,12 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
 
     for (;;) {
         // ---- refill idle lanes from the global cursor ----
-        // One atomicAdd per refill hands every idle lane the next consecutive ray.  (A per-warp pool of
-        // pre-reserved rays was measured slower: with queues of a few 100k rays the rays parked in the pools
-        // of busy warps are exactly the ones idle warps would need at the tail.)
+        // One atomicAdd per refill hands every idle lane the next consecutive ray.  kRefillBelow = 1: a warp takes
+        // 32 consecutive rays and finishes them all before fetching again.  Measured on B200 (cfg4 / dragon frame ms):
+        // refilling when fewer than 22 / 16 / 10 / 6 / 1 lanes are live gives 0.677 / 0.661 / 0.655 / 0.565 / 0.565 and
+        // 2.35 / 2.27 / 2.23 / 2.08 / 2.07; keeping every lane busy from a per-warp ring of prepared rays is slower still
+        // (0.67 / 2.74).  Rays that start together stay in phase (same tree levels, same leaves at the same time);
+        // a lane refilled mid-flight starts at the root while its neighbours are at leaves, and the warp pays for both.
         const unsigned idle = __ballot_sync(FULL, !have);
         if (idle && !exhausted) {
             const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
