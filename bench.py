@@ -205,6 +205,14 @@ def ours(args):
     trace_bytes = 48 * closest_rays + 32 * (cst["boxTests"] - cst["boxTestsShadow"]) + 48 * (cst["triTests"] - cst["triTestsShadow"])
     shadow_bytes = 48 * cst["shadowRays"] + 32 * cst["boxTestsShadow"] + 48 * cst["triTestsShadow"]
 
+    # the fast path's OWN work for the same frame (search-BVH nodes fetched, triangles tested), also untimed
+    wst_r = rb.Renderer(sc, device=local, walk_stats=True)
+    _, wst = wst_r.render()
+    wst_r.close()
+    own_bytes = [64 * wst["walkNodes"][k] + 48 * wst["walkTris"][k] + 64 * wst["walkEligibility"][k] for k in (0, 1)]
+    own_bytes[0] += 48 * closest_rays
+    own_bytes[1] += 48 * cst["shadowRays"]
+
     r = rb.Renderer(sc, device=local)
     out = torch.empty((h, w, 3), dtype=torch.float32, device="cuda") if world == 1 else None
     exchange = rdist.FrameExchange(h, w, args.strip_rows, rank, world, torch.device("cuda", local), args.transport) if world > 1 else None
@@ -335,6 +343,9 @@ def ours(args):
     except Exception:
         pass
 
+    kdom = 0 if dom == k_trace else 1
+    own = own_bytes[kdom] / max(1, world)
+    own_achieved = (own / launches_per_step) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
     head = e2e["bgr8"] if e2e.get("bgr8") else e2e["float"]
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
@@ -352,6 +363,13 @@ def ours(args):
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes / launches_per_step, "avg_launch_ms": avg_launch_ms,
                      "launches_per_step": launches_per_step,
+                     "own_work": {"bytes_per_launch": own / launches_per_step, "achieved": own_achieved, "unit": "GB/s",
+                                  "frac_of_hbm_peak": own_achieved / peak if peak else None,
+                                  "nodes_fetched": wst["walkNodes"][kdom], "triangles_tested": wst["walkTris"][kdom],
+                                  "eligibility_evaluations": wst["walkEligibility"][kdom],
+                                  "note": "what THIS kernel's algorithm touches: 64 B per search-BVH node fetched + 48 B per triangle "
+                                          "tested + 64 B per eligibility evaluation + 48 B per ray; served almost entirely from L1/L2 "
+                                          "(see traffic for the DRAM share), so it is a cache-bandwidth figure quoted against the HBM peak"},
                      "note": "bytes = 48/ray + 32/box test + 48/triangle test with the REFERENCE's work counts (SURVEY.md 8d): a work-"
                              "normalised yardstick, not DRAM traffic (the fast path tests ~1/100 of the reference's triangles and the "
                              "geometry is L2-resident), hence frac > 1; durations from a handle with per-launch CUDA events "

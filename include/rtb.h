@@ -154,6 +154,9 @@ typedef struct RtbStats {
     float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */
     float    msKernel[RTB_NKINDS];                /* device time per kernel kind (RTB_CREATE_KERNEL_TIMING) */
     uint32_t launchesKernel[RTB_NKINDS];
+    /* the fast path's OWN work (RTB_CREATE_WALK_STATS): search-BVH nodes fetched (64 B each), triangles tested (48 B
+     * each), eligibility evaluations; index 0 = closest-hit rays, 1 = shadow rays                                       */
+    uint64_t walkNodes[2], walkTris[2], walkEligibility[2];
 } RtbStats;
 
 typedef struct RtbHandle RtbHandle;
@@ -188,6 +191,7 @@ const char* rtb_host_last_error(void);
 #define RTB_CREATE_DEFAULT   0u
 #define RTB_CREATE_COUNTERS  (1u << 0)   /* count box / triangle tests (slower; parity of work)   */
 #define RTB_CREATE_EXACT_WALK (1u << 1)  /* traverse exactly like objects.cpp:587-631 (no culling) */
+#define RTB_CREATE_WALK_STATS (1u << 3)  /* fill RtbStats.walkNodes / walkTris / walkEligibility (slower kernels)    */
 #define RTB_CREATE_KERNEL_TIMING (1u << 2) /* fill RtbStats.msKernel: CUDA events around every launch (costs ~6 us
                                               of stream time per launch, so it is off by default)               */
 

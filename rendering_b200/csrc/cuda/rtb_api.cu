@@ -338,6 +338,7 @@ void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixel
 {
     const bool count = h->createFlags & RTB_CREATE_COUNTERS;
     const bool exact = h->createFlags & RTB_CREATE_EXACT_WALK;
+    const bool walkStats = h->createFlags & RTB_CREATE_WALK_STATS;
     const rt::Scene& sc = h->scene;
     const size_t smem = stackBytes(h);
     const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
@@ -353,6 +354,14 @@ void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixel
             KernelSpan ks(h, st, RTB_K_TRACE);
             if (count) rtk::k_trace<rtk::MODE_COUNT><<<gridFor(h, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, h->dFrame(), lv);
             else if (exact) rtk::k_trace<rtk::MODE_EXACT><<<gridFor(h, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, h->dFrame(), lv);
+            else if (walkStats) {   // same traversal with its own work counters (RTB_CREATE_WALK_STATS)
+                if (depth == 0 && genKind == rtk::GEN_PRIMARY)
+                    rtk::k_walk<false, rtk::GEN_PRIMARY, true><<<persistentGrid(h, 1, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
+                else if (depth == 0 && genKind == rtk::GEN_SSAA)
+                    rtk::k_walk<false, rtk::GEN_SSAA, true><<<persistentGrid(h, 2, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
+                else
+                    rtk::k_walk<false, rtk::GEN_QUEUE, true><<<persistentGrid(h, 0, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
+            }
             else if (depth == 0 && genKind == rtk::GEN_PRIMARY)
                 rtk::k_walk<false, rtk::GEN_PRIMARY><<<persistentGrid(h, 1, cap), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
             else if (depth == 0 && genKind == rtk::GEN_SSAA)
@@ -373,6 +382,7 @@ void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixel
                 KernelSpan ks(h, st, RTB_K_SHADOW);
                 if (count) rtk::k_shadow<rtk::MODE_COUNT><<<gridFor(h, maxShadow), rtk::kBlock, smem, st>>>(sc, q, surf, vis, h->dFrame(), lv);
                 else if (exact) rtk::k_shadow<rtk::MODE_EXACT><<<gridFor(h, maxShadow), rtk::kBlock, smem, st>>>(sc, q, surf, vis, h->dFrame(), lv);
+                else if (walkStats) rtk::k_walk<true, rtk::GEN_QUEUE, true><<<persistentGrid(h, 3, maxShadow), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
                 else rtk::k_walk<true, rtk::GEN_QUEUE><<<persistentGrid(h, 3, maxShadow), rtk::kBlock, smem, st>>>(sc, q, (int)cap, hits, surf, vis, h->dFrame(), lv, gen);
                 ks.done();
             }
@@ -423,6 +433,11 @@ int finishFrame(RtbHandle* h, cudaStream_t st, int passes)
             if (lv->nRays > 0) h->stats.levels = std::max<uint32_t>(h->stats.levels, (uint32_t)l + 1);
         }
     h->stats.shadowRaysSkipped = fc->shadowSkipped;
+    for (int k = 0; k < 2; ++k) {
+        h->stats.walkNodes[k] = fc->walkNodes[k];
+        h->stats.walkTris[k] = fc->walkTris[k];
+        h->stats.walkEligibility[k] = fc->walkEligibility[k];
+    }
     h->stats.ssaaPixels = (uint64_t)fc->ssaaPixels;
     if (h->createFlags & RTB_CREATE_COUNTERS) {
         h->stats.boxTestsShadow = fc->boxTestsShadow;

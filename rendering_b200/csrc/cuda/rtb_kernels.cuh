@@ -43,6 +43,8 @@ struct FrameCtr {
     int acMax;           // showAC debug view: largest per-pixel box count
     unsigned long long boxTests, triTests;             // closest-hit rays (counting build)
     unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (counting build)
+    // fast path's own work (RTB_CREATE_WALK_STATS): search-BVH nodes fetched, triangles tested, eligibility evaluations
+    unsigned long long walkNodes[2], walkTris[2], walkEligibility[2];   // [0] closest-hit rays, [1] shadow rays
 };
 enum { OVF_RAYS = 1, OVF_INTERIORS = 2, OVF_FLAGGED = 4 };
 
@@ -405,7 +407,7 @@ struct GenArgs {
 __device__ __noinline__ V3 genCameraRay(const Scene* sc, float px, float py) { return cameraDir(*sc, px, py); }
 __device__ __noinline__ void storeMissColour(const Scene* sc, float* slots, int dest, V3 d) { storeSlot(slots, dest, skybox(*sc, d)); }
 
-template <bool ANY, int GEN>
+template <bool ANY, int GEN, bool STATS = false>
 __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
     unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv, GenArgs gen)
 {
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
     int slotBest = 0x7fffffff, triM = -1;
     float tM = FLT_MAX, uM = 0.f, vM = 0.f;
     unsigned nSkipped = 0;
+    unsigned long long nNodes = 0, nTris = 0, nElig = 0;   // STATS only
 
     for (;;) {
         // ---- refill idle lanes from the global cursor ----
@@ -570,6 +573,7 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
                     while (cur >= 0) {
                         const float4* nd = me->bvhNodes + (size_t)cur * 4;
                         const float4 a = __ldg(nd), b = __ldg(nd + 1), c = __ldg(nd + 2), d = __ldg(nd + 3);
+                        if (STATS) nNodes++;
                         const float tFar = ANY ? tNear : tM;
                         bool h0, h1;
                         const float e0 = slabEntry(r, a.x, a.y, a.z, a.w, b.x, b.y, tFar, h0);
@@ -594,11 +598,14 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
                         for (int k = 0; k < count; ++k, tp += 3) {
                             const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
                             float t, u, v;
+                            if (STATS) nTris++;
                             if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
                             const int tri = __float_as_int(p0.w);
                             if (ANY) {
+                                if (STATS && t < tNear) nElig++;
                                 if (t < tNear && eligibleSlot(sc, *me, r, tri) >= 0) { blocked = true; break; }
                             } else if (t < tM || (found && t == tM)) {
+                                if (STATS) nElig++;
                                 const int slot = eligibleSlot(sc, *me, r, tri);
                                 if (slot >= 0 && (t < tM || slot < slotBest)) { tM = t; uM = u; vM = v; triM = tri; slotBest = slot; found = true; }
                             }
@@ -619,6 +626,11 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
         }
     }
     if (ANY && nSkipped) atomicAdd(&ctr->shadowSkipped, nSkipped);
+    if (STATS) {
+        atomicAdd(&ctr->walkNodes[ANY ? 1 : 0], nNodes);
+        atomicAdd(&ctr->walkTris[ANY ? 1 : 0], nTris);
+        atomicAdd(&ctr->walkEligibility[ANY ? 1 : 0], nElig);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -121,6 +121,20 @@ def test_default_handle_equals_counting_handle():
     assert np.array_equal(f2.view(np.uint32), fb.view(np.uint32))
 
 
+def test_walk_stats_handle_counts_its_own_work_and_renders_the_same_bits():
+    # RTB_CREATE_WALK_STATS: the fast path with its own counters must not change the image, and its work must be a small
+    # fraction of the reference walk's (that is the point of the search BVH)
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    sc = load("cfgD_dragon_1080", 160, 92)
+    a, sa = rb.Renderer(sc).render()
+    b, sb = rb.Renderer(sc, walk_stats=True).render()
+    _, sc_ = rb.Renderer(sc, counters=True).render()
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert sum(sa["walkNodes"]) == 0 and sb["walkNodes"][0] > 0 and sb["walkNodes"][1] > 0
+    assert 0 < sum(sb["walkTris"]) < sc_["triTests"] / 50
+
+
 def test_mixed_scene_every_material_and_area_light():
     sc = rb.Scene(text=MIXED_SCENE)
     check_against_oracle(sc, exact=False)
