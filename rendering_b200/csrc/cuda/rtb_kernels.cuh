@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQue
 // warp pulls rays from a global cursor, and whenever fewer than kRefillBelow lanes of the warp still hold
 // a live ray the finished lanes are refilled (ballot + one atomicAdd per warp), so a few long rays never
 // leave the other lanes idle.
-// Traversal is while-while over the search BVH with the per-thread stack in shared memory.
+// Traversal of the search BVH uses a per-thread stack in shared memory and the decoupled stepping described at the loop.
 //
 // GEN selects where closest-hit rays come from:
 //   GEN_QUEUE    the level's ray queue (secondary rays, caller-supplied rays)
@@ -389,6 +389,13 @@ constexpr int kDone = (int)0x80000000;   // cursor value: no mesh traversal in p
 #define RTB_REFILL_BELOW 1
 #endif
 constexpr int kRefillBelow = RTB_REFILL_BELOW;
+#ifndef RTB_LEAF_BATCH
+#define RTB_LEAF_BATCH 4
+#endif
+#ifndef RTB_INNER_STEPS
+#define RTB_INNER_STEPS 8
+#endif
+constexpr int kLeafBatch = RTB_LEAF_BATCH, kInnerSteps = RTB_INNER_STEPS;
 
 enum { GEN_QUEUE = 0, GEN_PRIMARY = 1, GEN_SSAA = 2 };
 
@@ -568,9 +575,22 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
                             obj++;
                         }
                     }
-                } else {
-                    // inner nodes
-                    while (cur >= 0) {
+                }
+            }
+            // Decoupled stepping.  A classic while-while loop lets every lane descend until ALL lanes of the warp have
+            // reached a leaf, so one long descent stalls 31 parked lanes, and then runs the triangle code for whoever
+            // has a leaf.  Here a round advances the lanes at inner nodes by at most kInnerSteps nodes, and lanes that
+            // reached a leaf park until kLeafBatch of them wait (or no lane can descend): nobody waits for a whole
+            // descent, and the triangle code runs for a group of lanes.  Measured on B200 against the while-while loop:
+            // dragon frame 2.07 -> 1.43 ms, cfg4 0.565 -> 0.52 ms (kInnerSteps 8, kLeafBatch 1..4 equivalent; 1 inner
+            // step per round or batches of 16+ leaves are 10-15 % slower).
+            {
+                const bool atInner = have && cur >= 0;
+                const bool atLeaf = have && cur < 0 && cur != kDone;
+                const unsigned innerM = __ballot_sync(FULL, atInner), leafM = __ballot_sync(FULL, atLeaf);
+                const bool runInner = innerM != 0 && __popc(leafM) < kLeafBatch;
+                if (runInner && atInner) {
+                    for (int step = 0; step < kInnerSteps && cur >= 0; ++step) {
                         const float4* nd = me->bvhNodes + (size_t)cur * 4;
                         const float4 a = __ldg(nd), b = __ldg(nd + 1), c = __ldg(nd + 2), d = __ldg(nd + 3);
                         if (STATS) nNodes++;
@@ -589,33 +609,34 @@ __global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, 
                         else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
                         else { cur = kDone; break; }
                     }
-                    // one leaf
-                    if (cur != kDone) {
-                        const int code = ~cur;
-                        const int first = code >> 3, count = (code & 7) + 1;
-                        const float4* tp = me->bvhTris + (size_t)first * 3;
-                        bool blocked = false;
-                        for (int k = 0; k < count; ++k, tp += 3) {
-                            const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-                            float t, u, v;
-                            if (STATS) nTris++;
-                            if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
-                            const int tri = __float_as_int(p0.w);
-                            if (ANY) {
-                                if (STATS && t < tNear) nElig++;
-                                if (t < tNear && eligibleSlot(sc, *me, r, tri) >= 0) { blocked = true; break; }
-                            } else if (t < tM || (found && t == tM)) {
-                                if (STATS) nElig++;
-                                const int slot = eligibleSlot(sc, *me, r, tri);
-                                if (slot >= 0 && (t < tM || slot < slotBest)) { tM = t; uM = u; vM = v; triM = tri; slotBest = slot; found = true; }
-                            }
-                        }
-                        if (ANY && blocked) { vis[out] = 0; have = false; cur = kDone; }
-                        else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
-                        else cur = kDone;
+                    if (cur == kDone) {   // mesh finished
+                        if (!ANY && found) { tNear = tM; uN = uM; vN = vM; objN = obj; triN = triM; }
+                        obj++;
                     }
-                    // mesh finished: fold into the running best (`tNear < intrInfo.tNear`, scene.cpp:740)
-                    if (have && cur == kDone) {
+                } else if (!runInner && atLeaf) {
+                    const int code = ~cur;
+                    const int first = code >> 3, count = (code & 7) + 1;
+                    const float4* tp = me->bvhTris + (size_t)first * 3;
+                    bool blocked = false;
+                    for (int k = 0; k < count; ++k, tp += 3) {
+                        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                        float t, u, v;
+                        if (STATS) nTris++;
+                        if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
+                        const int tri = __float_as_int(p0.w);
+                        if (ANY) {
+                            if (STATS && t < tNear) nElig++;
+                            if (t < tNear && eligibleSlot(sc, *me, r, tri) >= 0) { blocked = true; break; }
+                        } else if (t < tM || (found && t == tM)) {
+                            if (STATS) nElig++;
+                            const int slot = eligibleSlot(sc, *me, r, tri);
+                            if (slot >= 0 && (t < tM || slot < slotBest)) { tM = t; uM = u; vM = v; triM = tri; slotBest = slot; found = true; }
+                        }
+                    }
+                    if (ANY && blocked) { vis[out] = 0; have = false; cur = kDone; }
+                    else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
+                    else {
+                        cur = kDone;
                         if (!ANY && found) { tNear = tM; uN = uM; vN = vM; objN = obj; triN = triM; }
                         obj++;
                     }
