@@ -830,8 +830,8 @@ __global__ void __launch_bounds__(kBlock) k_sobel(int width, int height, const f
     // one warp = one 8x4 pixel tile; its 10x6 pixel neighbourhood (180 floats per channel row) is staged in shared
     // memory with coalesced row loads when the tile's four rows are consecutive image rows (always, unless a strip
     // partition cuts through the tile); otherwise every lane reads its 3x3 window directly
-    __shared__ float tileMem[kBlock / 32][6][32];
-    float (*tile)[32] = tileMem[threadIdx.x >> 5];
+    __shared__ float tileMem[kBlock / 32][6][33];      // rows padded to 33 floats: the 4 pixel rows of a warp hit different banks
+    float (*tile)[33] = tileMem[threadIdx.x >> 5];
     const int tilesX = (width + 7) / 8;
     const long long total = (long long)tilesX * ((nRows + 3) / 4) * 32;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {

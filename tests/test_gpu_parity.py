@@ -145,12 +145,17 @@ def test_mixed_scene_every_material_and_area_light():
     ("useBackfaceCulling=0", True),
     ("useAC=0", True),
     ("max_ray_depth=0", False),
+    ("useTextures=0", False),
     ("rotation=10,25,-5\nposition=0.3,0.2,1", True),
 ])
 def test_option_switches(opts, exact):
     if HAVE_ASSETS:
         sc = load("cfg2_smooth_shading_1024", 160, 120, extra_options=opts)
         check_against_oracle(sc, exact)
+        if opts == "useTextures=0":      # the three shotgun maps are skipped at load (objects.cpp:398,419,441)
+            sc = load("cfg4_shotgun_1080", 200, 112, extra_options=opts)
+            assert not sc.desc.meshes[0].diffuseMap.rgb
+            check_against_oracle(sc, exact=False)
     sc = rb.Scene(text=MIXED_SCENE.replace("[options]\n", "[options]\n" + opts + "\n"))
     check_against_oracle(sc, exact=(opts == "showNormals=1"))
 
