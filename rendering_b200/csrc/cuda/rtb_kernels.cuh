@@ -4,16 +4,21 @@
 // frame is a sequence of breadth-first LEVELS (level = recursion depth); each level runs as
 // separate kernels over compacted queues:
 //
-//   k_raygen / k_ssaa_gen   primary rays                      (renderWorker, SSAAworker)
-//   k_trace                 closest hit over all objects      (Render::trace + intersectAccelStruct)
-//   k_surface               hit -> surface record, miss -> skybox; compacts hits   (castRay :762-775, :945)
-//   k_shadow                any-hit shadow rays, one per (surface, light sample)   (castRay :785-787 ...)
+//   k_walk<false, GEN>      closest hit over all objects (Render::trace + the search BVH); generates the primary
+//                           and SSAA rays itself (renderWorker, SSAAworker) and resolves their misses
+//   k_surface               hit -> surface record (compacts hits); misses of queued rays -> skybox   (castRay :762-775, :945)
+//   k_walk<true>            any-hit shadow rays, one per (surface, light sample)   (castRay :785-787 ...)
 //   k_shade                 light accumulation per material; resolves Diffuse/Phong, spawns the
 //                           Reflective / Transparent children into the next level's queue
 //   k_combine               folds child colours into their parents, deepest level first, with the
 //                           reference's exact expression order (:858-890, :896-940)
 //   k_sobel                 edge mask + compaction of flagged pixels   (launchSSAA :554-568)
 //   k_ssaa_resolve          mean of the 4 re-traced samples            (SSAAworker :525-536)
+//   k_fill_background, k_gather_rows / k_scatter_rows / k_quantize_bgr8, k_count_ac / k_ac_resolve, k_rgb_to_rgba
+//                           frame pre-fill, output stages (incl. saveImage's conversion), showAC view, texture upload
+//   k_raygen, k_ssaa_gen, k_trace, k_shadow
+//                           the LITERAL reference walk (objects.cpp:587-631) over materialised queues: parity of the
+//                           reference's work counters (RTB_CREATE_COUNTERS / RTB_CREATE_EXACT_WALK), not the timed path
 //
 // Colours travel through a "slot" array (3 floats per slot): slots [0, w*h) are the framebuffer,
 // the rest is bump-allocated for SSAA samples and for the children of Reflective / Transparent hits.
@@ -373,9 +378,8 @@ __global__ void __launch_bounds__(kBlock) k_shadow(Scene sc, RayQueue q, SurfQue
 // One kernel serves both ray kinds: ANY = false is Render::trace for primary / secondary rays
 // (closest hit over all objects), ANY = true is the shadow trace (any occluder closer than the
 // light, Transparent objects skipped).  The grid is sized to the machine, not to the queue: every
-// warp pulls rays from a global cursor, and whenever fewer than kRefillBelow lanes of the warp still hold
-// a live ray the finished lanes are refilled (ballot + one atomicAdd per warp), so a few long rays never
-// leave the other lanes idle.
+// warp pulls batches of consecutive rays from a global cursor (ballot + one atomicAdd per warp) whenever fewer
+// than kRefillBelow of its lanes still hold a live ray (1 = finish the batch first, measured best; see the loop).
 // Traversal of the search BVH uses a per-thread stack in shared memory and the decoupled stepping described at the loop.
 //
 // GEN selects where closest-hit rays come from:
