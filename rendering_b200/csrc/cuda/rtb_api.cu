@@ -196,52 +196,14 @@ int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
     d.triRefOff = upload(h, fp.triRefOff.data(), fp.triRefOff.size());
     d.triRefs = upload(h, fp.triRefs.data(), fp.triRefs.size());
     d.parent = upload(h, fp.parent.data(), fp.parent.size());
-    if (!fp.nodes.empty() && m.nTris > 0) {
-        const rtbvh::Node& root = fp.nodes[0];
-        std::array<float, 6> b;
-        for (int a = 0; a < 3; ++a) {
-            b[a] = std::min(root.c0lo[a], root.c1lo[a]);          // an empty child has lo = +FLT_MAX, hi = -FLT_MAX
-            b[3 + a] = std::max(root.c0hi[a], root.c1hi[a]);
-        }
-        h->geomBounds.push_back(b);
-    }
+    std::array<float, 6> b;
+    if (rtpack::meshBounds(fp, b)) h->geomBounds.push_back(b);
     return fp.maxDepth;
 }
 
-// Pixel rectangle that contains the projection of every bounded object, expanded by 2 pixels (the projection uses
-// the camera constants in double; rounding is ~1e-4 pixel).  The whole rendered frame when anything is unbounded,
-// behind / around the camera, or when missing rays need their direction.
 void computePrimaryRect(RtbHandle* h)
 {
-    const rt::Scene& sc = h->scene;
-    const int wm1 = sc.width - 1, hm1 = sc.height - 1;
-    int* r = h->primRect;
-    r[0] = 0; r[1] = wm1; r[2] = 0; r[3] = hm1;
-    if (h->unbounded || (sc.flags & rt::FLAG_SKYBOX)) return;
-    double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
-    for (const auto& b : h->geomBounds) {
-        for (int c = 0; c < 8; ++c) {
-            const double v[3] = { (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, (double)b[(c & 4) ? 5 : 2] - sc.camPos.z };
-            if (!(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]))) return;
-            // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
-            double cam[3];
-            for (int i = 0; i < 3; ++i) cam[i] = v[0] * sc.camM[i * 4 + 0] + v[1] * sc.camM[i * 4 + 1] + v[2] * sc.camM[i * 4 + 2];
-            const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-            if (!(cam[2] < -1e-4 * len)) return;                   // at or behind the camera plane: no bound
-            const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
-            // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
-            const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
-            const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
-            if (!(std::isfinite(px) && std::isfinite(py))) return;
-            minX = std::min(minX, px); maxX = std::max(maxX, px);
-            minY = std::min(minY, py); maxY = std::max(maxY, py);
-        }
-    }
-    if (h->geomBounds.empty()) { r[0] = r[1] = r[2] = r[3] = 0; return; }
-    auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
-    r[0] = clampi(std::floor(minX) - 2, 0, wm1); r[1] = clampi(std::ceil(maxX) + 3, 0, wm1);
-    r[2] = clampi(std::floor(minY) - 2, 0, hm1); r[3] = clampi(std::ceil(maxY) + 3, 0, hm1);
-    if (r[1] <= r[0] || r[3] <= r[2]) r[0] = r[1] = r[2] = r[3] = 0;
+    rtpack::primaryRect(h->scene, h->geomBounds, h->unbounded, h->primRect);
 }
 
 size_t stackBytes(const RtbHandle* h) { return (size_t)h->stackEntries * rtk::kBlock * sizeof(int); }
@@ -753,15 +715,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             if (m.nNodes > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
             meshes.push_back(d);
         }
-        for (int i = 0; i < s->nObjects; ++i) {
-            const RtbObject& o = s->objects[i];
-            if (o.type == RTB_OBJ_PLANE) h->unbounded = true;
-            else if (o.type == RTB_OBJ_SPHERE) {
-                const float rad = std::sqrt(std::max(0.0f, o.r2)) * 1.001f + 1e-6f;
-                if (!(rad < FLT_MAX)) h->unbounded = true;
-                h->geomBounds.push_back({ o.pos[0] - rad, o.pos[1] - rad, o.pos[2] - rad, o.pos[0] + rad, o.pos[1] + rad, o.pos[2] + rad });
-            }
-        }
+        for (int i = 0; i < s->nObjects; ++i) rtpack::objectBounds(s->objects[i], h->geomBounds, h->unbounded);
         computePrimaryRect(h);
         // recursion levels: only Reflective / Transparent hits spawn children (scene.cpp:854-941)
         bool spawns = false;

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
@@ -105,6 +106,63 @@ inline void packFastPath(const RtbMesh& m, FastPath& out)
         const RtbNode& n = m.nodes[k];
         if (n.right >= 0) continue;
         for (int s = n.firstRef; s < n.firstRef + n.refCount; ++s) out.triRefs[cursor[m.refs[s]]++] = int2{ k, s };
+    }
+}
+
+// Pixel rectangle {x0, x1, y0, y1} (columns [x0,x1), rows [y0,y1)) that contains the projection of every bounded
+// object, expanded by 2 pixels (the projection uses the camera constants in double; rounding is ~1e-4 pixel).
+// The whole rendered frame when anything is unbounded, behind / around the camera, or when missing rays need their
+// direction (skybox).  bounds: world-space boxes lo.xyz, hi.xyz around everything a primary ray can hit.
+inline void primaryRect(const rt::Scene& sc, const std::vector<std::array<float, 6>>& bounds, bool unbounded, int r[4])
+{
+    const int wm1 = sc.width - 1, hm1 = sc.height - 1;
+    r[0] = 0; r[1] = wm1; r[2] = 0; r[3] = hm1;
+    if (unbounded || (sc.flags & rt::FLAG_SKYBOX)) return;
+    double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
+    for (const auto& b : bounds) {
+        for (int c = 0; c < 8; ++c) {
+            const double v[3] = { (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, (double)b[(c & 4) ? 5 : 2] - sc.camPos.z };
+            if (!(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]))) return;
+            // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
+            double cam[3];
+            for (int i = 0; i < 3; ++i) cam[i] = v[0] * sc.camM[i * 4 + 0] + v[1] * sc.camM[i * 4 + 1] + v[2] * sc.camM[i * 4 + 2];
+            const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            if (!(cam[2] < -1e-4 * len)) return;                   // at or behind the camera plane: no bound
+            const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
+            // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
+            const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
+            const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
+            if (!(std::isfinite(px) && std::isfinite(py))) return;
+            minX = std::min(minX, px); maxX = std::max(maxX, px);
+            minY = std::min(minY, py); maxY = std::max(maxY, py);
+        }
+    }
+    if (bounds.empty()) { r[0] = r[1] = r[2] = r[3] = 0; return; }
+    auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
+    r[0] = clampi(std::floor(minX) - 2, 0, wm1); r[1] = clampi(std::ceil(maxX) + 3, 0, wm1);
+    r[2] = clampi(std::floor(minY) - 2, 0, hm1); r[3] = clampi(std::ceil(maxY) + 3, 0, hm1);
+    if (r[1] <= r[0] || r[3] <= r[2]) r[0] = r[1] = r[2] = r[3] = 0;
+}
+
+// The bounds primaryRect needs: the padded root box of a mesh's search BVH ...
+inline bool meshBounds(const FastPath& fp, std::array<float, 6>& b)
+{
+    if (fp.nodes.empty() || fp.tris.empty()) return false;
+    const rtbvh::Node& root = fp.nodes[0];
+    for (int a = 0; a < 3; ++a) {
+        b[a] = std::min(root.c0lo[a], root.c1lo[a]);          // an empty child has lo = +FLT_MAX, hi = -FLT_MAX
+        b[3 + a] = std::max(root.c0hi[a], root.c1hi[a]);
+    }
+    return true;
+}
+// ... a box around a sphere; a plane makes the scene unbounded
+inline void objectBounds(const RtbObject& o, std::vector<std::array<float, 6>>& bounds, bool& unbounded)
+{
+    if (o.type == RTB_OBJ_PLANE) unbounded = true;
+    else if (o.type == RTB_OBJ_SPHERE) {
+        const float rad = std::sqrt(std::max(0.0f, o.r2)) * 1.001f + 1e-6f;
+        if (!(rad < FLT_MAX)) unbounded = true;
+        bounds.push_back({ o.pos[0] - rad, o.pos[1] - rad, o.pos[2] - rad, o.pos[0] + rad, o.pos[1] + rad, o.pos[2] + rad });
     }
 }
 

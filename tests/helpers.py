@@ -38,6 +38,8 @@ def shim():
     if _shim is None:
         lib = C.CDLL(os.path.join(ROOT, "tests", "shim", "libshim.so"))
         lib.shim_render.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.shim_render_fast.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.shim_primary_rect.argtypes = [C.POINTER(_ffi.RtbScene), C.POINTER(C.c_int)]
         _shim = lib
     return _shim
 
@@ -53,12 +55,19 @@ def oracle_render(scene, threads=None):
     return p1, fin, dict(zip(["rays", "boxTests", "triTests", "ssaaPixels"], [int(c) for c in cnt]))
 
 
-def shim_render(scene):
+def shim_primary_rect(scene):
+    """-> (x0, x1, y0, y1): pixel columns / rows the CUDA path generates primary rays for"""
+    rect = (C.c_int * 4)()
+    shim().shim_primary_rect(scene.view, rect)
+    return tuple(rect)
+
+
+def shim_render(scene, fast=False):
     h, w = scene.height, scene.width
     p1 = np.zeros((h, w, 3), np.float32)
     fin = np.zeros((h, w, 3), np.float32)
     cnt = (C.c_uint64 * 4)()
-    shim().shim_render(scene.view, p1.ctypes.data, fin.ctypes.data, cnt)
+    (shim().shim_render_fast if fast else shim().shim_render)(scene.view, p1.ctypes.data, fin.ctypes.data, cnt)
     return p1, fin, dict(zip(["rays", "boxTests", "triTests", "ssaaPixels"], [int(c) for c in cnt]))
 
 

@@ -165,6 +165,25 @@ int shim_render(const RtbScene* s, float* pass1, float* final, unsigned long lon
 // same, but meshes are searched through the fast path (search BVH + eligibility tables)
 int shim_render_fast(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4]) { return render_impl(s, pass1, final, counters, true); }
 
+// the pixel rectangle primary rays are limited to (scene_pack.h primaryRect), computed exactly like rtb_create does
+int shim_primary_rect(const RtbScene* s, int rect[4])
+{
+    rt::Scene sc;
+    rtpack::packHeader(*s, sc);
+    std::vector<std::array<float, 6>> bounds;
+    bool unbounded = false;
+    for (int i = 0; i < s->nMeshes; ++i) {
+        if (s->meshes[i].nNodes == 0) continue;
+        rtpack::FastPath fp;
+        rtpack::packFastPath(s->meshes[i], fp);
+        std::array<float, 6> b;
+        if (rtpack::meshBounds(fp, b)) bounds.push_back(b);
+    }
+    for (int i = 0; i < s->nObjects; ++i) rtpack::objectBounds(s->objects[i], bounds, unbounded);
+    rtpack::primaryRect(sc, bounds, unbounded, rect);
+    return 0;
+}
+
 } // extern "C"
 
 static int render_impl(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4], bool fast)

@@ -1,0 +1,93 @@
+"""The fast path's ALGORITHM on the CPU box (no GPU): the search BVH + eligibility tables of scene_pack.h /
+bvh_build.h driven through rt_device.cuh's walkMeshFast (tests/shim), and the screen-space bounds primary rays are
+limited to.  The kernels' own plumbing is covered by the -m gpu tests; this pins the parts that are plain host-compilable
+code against the oracle before a GPU is involved."""
+import numpy as np
+import pytest
+
+import rendering_b200 as rb
+from helpers import HAVE_ASSETS, golden_case, load, needs_assets, oracle_render, shim_primary_rect, shim_render, GOLDEN
+
+
+@pytest.mark.parametrize("name", ["cfg2_128", "cfg4_240", "cfgD_160"])
+def test_search_bvh_with_eligibility_equals_the_literal_walk(name):
+    if needs_assets(GOLDEN[name]["scene"]) and not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    g, sc, _ = golden_case(name)
+    a1, afin, acnt = shim_render(sc)                 # literal reference walk (objects.cpp:587-631)
+    b1, bfin, bcnt = shim_render(sc, fast=True)      # binned-SAH search BVH + exact eligibility of the reference tree
+    assert np.array_equal(a1.view(np.uint32), b1.view(np.uint32))
+    assert np.array_equal(afin.view(np.uint32), bfin.view(np.uint32))
+    assert acnt["rays"] == bcnt["rays"] == g["rays"] and acnt["ssaaPixels"] == bcnt["ssaaPixels"]
+
+
+@pytest.mark.parametrize("opts", ["", "useBackfaceCulling=0", "useAC=0", "rotation=7,31,-4\nposition=0.4,0.1,0.6"])
+def test_search_bvh_option_switches(opts):
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    # shotgun: 362 of its 1539 triangles poke outside the reference root box -> eligibility matters
+    sc = load("cfg4_shotgun_1080", 120, 68, extra_options=opts)
+    a1, afin, _ = shim_render(sc)
+    b1, bfin, _ = shim_render(sc, fast=True)
+    assert np.array_equal(a1.view(np.uint32), b1.view(np.uint32)) and np.array_equal(afin.view(np.uint32), bfin.view(np.uint32))
+
+
+BOUNDED = """
+[options]
+width=160
+height=120
+background_color=0.25,0.5,0.75
+{camera}
+[light]
+type=point
+position=-1,3,1
+intensity=0.8
+[object]
+type=sphere
+pos=-0.8,0.2,-4
+radius=0.7
+color=0.9,0.3,0.2
+[object]
+type=sphere
+pos=1.1,-0.3,-5
+radius=1.1
+color=0.2,0.8,0.4
+[end]
+"""
+
+
+def _check_rect(sc):
+    x0, x1, y0, y1 = shim_primary_rect(sc)
+    p1, _, _ = oracle_render(sc)
+    bg = np.ctypeslib.as_array(sc.desc.backgroundColor).astype(np.float32)
+    hit = (p1[:-1, :-1] != bg).any(axis=2)           # rendered pixels that are not a plain miss
+    ys, xs = np.nonzero(hit)
+    if len(ys):
+        assert xs.min() >= x0 and xs.max() < x1 and ys.min() >= y0 and ys.max() < y1, ((x0, x1, y0, y1), xs.min(), xs.max(), ys.min(), ys.max())
+    return (x0, x1, y0, y1), int(hit.sum())
+
+
+@pytest.mark.parametrize("camera", ["", "position=0.5,0.2,1\nrotation=4,-12,3", "fov=25", "fov=120", "rotation=0,35,0",
+                                    "rotation=0,170,0", "position=1.1,-0.3,-5", "position=-0.8,0.2,-3.2", "rotation=20,-40,15\nfov=90"])
+def test_primary_ray_bounds_contain_every_hit_pixel(camera):
+    sc = rb.Scene(text=BOUNDED.format(camera=camera))
+    rect, hits = _check_rect(sc)
+    w, h = sc.width, sc.height
+    if camera == "":
+        assert (rect[1] - rect[0]) * (rect[3] - rect[2]) < 0.5 * w * h and hits > 0     # the bound actually prunes
+    if camera == "position=1.1,-0.3,-5":
+        assert rect == (0, w - 1, 0, h - 1)                                            # camera inside a sphere: no bound
+
+
+def test_primary_ray_bounds_with_meshes_planes_and_skybox():
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    for cfg, extra in (("cfgD_dragon_1080", ""), ("cfgD_dragon_1080", "position=0.4,0.1,0.3\nrotation=0,25,0"), ("cfg4_shotgun_1080", ""),
+                       ("cfg4_shotgun_1080", "rotation=0,-20,10\nfov=40")):
+        sc = load(cfg, 192, 108, extra_options=extra)
+        _check_rect(sc)
+    full = lambda sc: (0, sc.width - 1, 0, sc.height - 1)
+    sc = load("cfg2_smooth_shading_1024", 64, 64)           # has a plane
+    assert shim_primary_rect(sc) == full(sc)
+    sc = load("cfg3_reflective_refractive_1080", 64, 36)    # skybox: a miss needs its direction
+    assert shim_primary_rect(sc) == full(sc)
