@@ -418,8 +418,11 @@ struct GenArgs {
 __device__ __noinline__ V3 genCameraRay(const Scene* sc, float px, float py) { return cameraDir(*sc, px, py); }
 __device__ __noinline__ void storeMissColour(const Scene* sc, float* slots, int dest, V3 d) { storeSlot(slots, dest, skybox(*sc, d)); }
 
+#ifndef RTB_WALK_MIN_BLOCKS
+#define RTB_WALK_MIN_BLOCKS 9   // 56 registers, 9 CTAs per SM: measured 1-2 % faster than 64 / 78 registers at 8 / 6 CTAs
+#endif
 template <bool ANY, int GEN, bool STATS = false>
-__global__ void __launch_bounds__(kBlock) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
+__global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
     unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv, GenArgs gen)
 {
     extern __shared__ int stackMem[];
