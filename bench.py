@@ -288,6 +288,8 @@ def ours(args):
             for i in range(args.steps + 2):
                 barrier()
                 t0 = time.perf_counter()
+                # the step's input is the camera: uploaded (host -> device) inside the timed region, as a frame loop does
+                r.set_camera_raw(sc.desc.camera)
                 if world == 1:
                     if name == "bgr8":
                         _, est = r.render_bgr8(out=host_px.numpy())
@@ -354,7 +356,7 @@ def ours(args):
         "config": {"workload": f"{args.scene}: {w}x{h} frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays,
                    "l2": "flushed between timed frames (256 MiB write)", "partition": (f"cyclic strips of {args.strip_rows} rows; exchange: " + ("NVLink stores into rank 0's symmetric-memory frame + 1 device barrier" if exchange.transport == "p2p" else "1 NCCL gather")) if world > 1 else "single GPU",
                    "timing": "CUDA events on the render stream per frame, summed; max over ranks"},
-        "e2e": dict(head, what=("rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes), wall clock"
+        "e2e": dict(head, what=("per frame: camera constants uploaded (rtb_set_camera), rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes), wall clock"
                                 if world == 1 else f"strips rendered per rank, exchanged to rank 0 ({exchange.transport}), converted to BMP pixel bytes there and copied to pinned host memory, wall clock")),
         "e2e_float": e2e["float"] if e2e.get("bgr8") else None,
         "gpu_launches": launches,

@@ -140,6 +140,10 @@ class Renderer:
             raise RtbError(rc, host.rtb_host_last_error().decode())
         self._check(self._lib.rtb_set_camera(self._h, C.byref(cam)))
 
+    def set_camera_raw(self, camera: "_ffi.RtbCamera") -> None:
+        """rtb_set_camera with ready-made constants (e.g. scene.desc.camera)."""
+        self._check(self._lib.rtb_set_camera(self._h, C.byref(camera)))
+
     def render_ac(self):
         """showAC debug view: (float32 frame (h, w, 3), int32 box counts (h, w), stats)."""
         fb = np.empty((self.height, self.width, 3), np.float32)

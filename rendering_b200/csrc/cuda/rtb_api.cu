@@ -92,6 +92,7 @@ struct RtbHandle {
     std::vector<std::array<float, 6>> geomBounds;
     bool unbounded = false;
     int primRect[4] = { 0, 0, 0, 0 };  // pixel columns [x0,x1) and rows [y0,y1) primary rays are generated for
+    uint64_t pendingH2D = 0;           // bytes uploaded by rtb_set_camera since the last render call (reported in its stats)
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
     int walkBlocksPerSm[4] = { 1, 1, 1, 1 };   // resident CTAs per SM of k_walk<false, GEN 0..2> / k_walk<true> with that stack
@@ -367,6 +368,8 @@ void beginCall(RtbHandle* h)
 {
     CK(cudaSetDevice(h->device));
     h->stats = RtbStats{};
+    h->stats.h2dBytes = h->pendingH2D;
+    h->pendingH2D = 0;
     h->spans.clear();
     h->eventsUsed = 0;
 }
@@ -758,6 +761,7 @@ int rtb_set_camera(RtbHandle* h, const RtbCamera* camera)
         h->scene.camAspect = camera->aspect;
         CK(cudaStreamSynchronize(h->ownStream));
         CK(cudaMemcpy(h->sceneDev, &h->scene, sizeof(rt::Scene), cudaMemcpyHostToDevice));
+        h->pendingH2D += sizeof(rt::Scene);
         computePrimaryRect(h);
         return RTB_OK;
     });
