@@ -190,3 +190,64 @@ radius=0.6
 color=0.2,0.8,0.3
 [end]
 """
+
+
+# Several meshes at once, each with a different material (glass bunny, mirror teapot, Phong icosahedron, Diffuse floor quad,
+# textured cow), point + distant light: exercises the object loop over meshes, secondary rays leaving and entering mesh
+# surfaces, shadow rays skipping the Transparent mesh, and the v//n / pentagon-fan / quad OBJ variants.
+MULTI_MESH_SCENE = """
+[options]
+width=144
+height=96
+background_color=0.3,0.45,0.6
+max_ray_depth=3
+ac_penalty=2
+[light]
+type=point
+position=-1,3,0.5
+intensity=0.9
+[light]
+type=distant
+direction=0.3,-1,-0.5
+color=1,0.95,0.9
+intensity=0.35
+[object]
+type=mesh
+pos=0,-1.2,-4.5
+size=7,1,7
+color=0.8,0.8,0.75
+name=input/objects/floor.obj
+[object]
+type=mesh
+pos=-1.3,-0.4,-4.2
+size=1.4,1.4,1.4
+rot=0,30,0
+color=1,1,1
+material=transparent,1.45
+name=input/objects/bunny.obj
+[object]
+type=mesh
+pos=1.2,-0.5,-4.6
+size=1.6,1.6,1.6
+rot=0,-40,0
+color=1,1,1
+material=reflective
+name=input/objects/teapot.obj
+[object]
+type=mesh
+pos=0.1,0.9,-5.5
+size=1.1,1.1,1.1
+rot=20,10,0
+color=0.9,0.6,0.2
+material=phong,0.2,0.5,0.6,20
+name=input/objects/icosahedron.obj
+[object]
+type=mesh
+pos=0,-0.6,-3.2
+size=1.0,1.0,1.0
+rot=0,200,0
+color=1,1,1
+name=input/objects/cow.obj
+diffuse_map=input/objects/cow_diffuse.bmp
+[end]
+"""

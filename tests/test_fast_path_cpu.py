@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import rendering_b200 as rb
-from helpers import HAVE_ASSETS, golden_case, load, needs_assets, oracle_render, shim_primary_rect, shim_render, GOLDEN
+from helpers import HAVE_ASSETS, MULTI_MESH_SCENE, diff_stats, golden_case, load, needs_assets, oracle_render, shim_primary_rect, shim_render, GOLDEN
 
 
 @pytest.mark.parametrize("name", ["cfg2_128", "cfg4_240", "cfgD_160"])
@@ -91,3 +91,18 @@ def test_primary_ray_bounds_with_meshes_planes_and_skybox():
     assert shim_primary_rect(sc) == full(sc)
     sc = load("cfg3_reflective_refractive_1080", 64, 36)    # skybox: a miss needs its direction
     assert shim_primary_rect(sc) == full(sc)
+
+
+def test_several_meshes_with_every_material_on_the_cpu():
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    sc = rb.Scene(text=MULTI_MESH_SCENE, asset_dir=rb.SCENES_DIR)
+    assert sc.desc.nMeshes == 5 and all(sc.tree_stats(i)["nodes"] >= 1 for i in range(5))
+    o1, ofin, ocnt = oracle_render(sc)
+    a1, afin, acnt = shim_render(sc)
+    b1, bfin, bcnt = shim_render(sc, fast=True)
+    assert acnt["rays"] == bcnt["rays"] == ocnt["rays"] and ocnt["rays"] > 3 * sc.width * sc.height
+    assert np.array_equal(a1.view(np.uint32), b1.view(np.uint32)) and np.array_equal(afin.view(np.uint32), bfin.view(np.uint32))
+    d = diff_stats(bfin, ofin)
+    assert d["rms"] <= 1e-4 and d["max_abs"] <= 2.5e-7, d
+    _check_rect(sc)

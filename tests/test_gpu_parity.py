@@ -15,7 +15,7 @@ import torch
 import rendering_b200 as rb
 import os
 
-from helpers import (GOLDEN, GOLDEN_DIR, HAVE_ASSETS, MIXED_SCENE, diff_stats, golden_case, load, needs_assets, oracle_cast,
+from helpers import (GOLDEN, GOLDEN_DIR, HAVE_ASSETS, MIXED_SCENE, MULTI_MESH_SCENE, diff_stats, golden_case, load, needs_assets, oracle_cast,
                      oracle_render, oracle_show_ac, oracle_trace)
 
 pytestmark = pytest.mark.gpu
@@ -133,6 +133,24 @@ def test_walk_stats_handle_counts_its_own_work_and_renders_the_same_bits():
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert sum(sa["walkNodes"]) == 0 and sb["walkNodes"][0] > 0 and sb["walkNodes"][1] > 0
     assert 0 < sum(sb["walkTris"]) < sc_["triTests"] / 50
+
+
+def test_several_meshes_with_every_material():
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    sc = rb.Scene(text=MULTI_MESH_SCENE, asset_dir=rb.SCENES_DIR)
+    fb, p1, st = check_against_oracle(sc, exact=False)
+    assert st["levels"] == 4 and st["secondaryRays"] > 0
+    r = rb.Renderer(sc)
+    full, _ = r.render()
+    part, _ = r.render(30, 61)
+    assert np.array_equal(part.view(np.uint32), full[30:61].view(np.uint32))
+    rng = np.random.default_rng(3)
+    rays = np.concatenate([rng.normal(size=(5000, 3)).astype(np.float32) * np.float32(0.2),
+                           (rng.normal(size=(5000, 3)) * [0.3, 0.3, 0.1] + [0, 0, -1]).astype(np.float32)], 1)
+    tuv, ot = r.trace(rays)
+    otuv, oot = oracle_trace(sc, rays)
+    assert np.array_equal(ot, oot) and np.array_equal(tuv[ot[:, 0] >= 0].view(np.uint32), otuv[oot[:, 0] >= 0].view(np.uint32))
 
 
 def test_mixed_scene_every_material_and_area_light():
