@@ -45,7 +45,7 @@ def build_host(force=False):
     out = os.path.join(HERE, "librtb_host.so")
     srcs = [os.path.join(CSRC, s) for s in HOST_SOURCES]
     if force or _stale(out, srcs + _glob_headers("host")):
-        _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra", *srcs, "-o", out, "-ldl"])
+        _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wall", "-Wextra", *srcs, "-o", out, "-ldl"])
     exe = os.path.join(HERE, "RayTracing")
     main = os.path.join(CSRC, "host/main.cpp")
     if force or _stale(exe, [main, out]):

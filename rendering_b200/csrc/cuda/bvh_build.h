@@ -16,7 +16,9 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <future>
 #include <vector>
 
 namespace rtbvh {
@@ -82,7 +84,8 @@ public:
             res_.nodes[0].child0 = res_.nodes[0].child1 = ~0;
             return res_;
         }
-        splitInto(0, 0, nTris, 1);
+        parallel_ = std::getenv("RTB_BVH_SERIAL") == nullptr;
+        splitInto(res_, 0, 0, nTris, 1);
         return res_;
     }
 
@@ -90,6 +93,7 @@ private:
     const float* pos_ = nullptr;
     float pad_ = 0;
     int maxLeaf_ = 4;
+    bool parallel_ = true;
     Result res_;
     std::vector<Box> boxes_;
     std::vector<float> cent_;
@@ -104,11 +108,31 @@ private:
         return b;
     }
 
-    int makeLeaf(int first, int last)
+    int makeLeaf(Result& res, int first, int last) const
     {
-        const int start = (int)res_.triOrder.size();
-        for (int i = first; i < last; ++i) res_.triOrder.push_back(ids_[i]);
+        const int start = (int)res.triOrder.size();
+        for (int i = first; i < last; ++i) res.triOrder.push_back(ids_[i]);
         return ~((start << 3) | (last - first - 1));
+    }
+
+    // appends a subtree built on its own (another thread) and returns the index its root got; inner links and
+    // leaf codes are shifted into `res`'s numbering, which reproduces the sequential (DFS) layout exactly
+    static int append(Result& res, const Result& sub)
+    {
+        const int nodeBase = (int)res.nodes.size(), triBase = (int)res.triOrder.size();
+        auto shift = [&](int child) {
+            if (child >= 0) return child + nodeBase;
+            const int code = ~child;
+            return ~((((code >> 3) + triBase) << 3) | (code & 7));
+        };
+        for (Node n : sub.nodes) {
+            n.child0 = shift(n.child0);
+            n.child1 = shift(n.child1);
+            res.nodes.push_back(n);
+        }
+        res.triOrder.insert(res.triOrder.end(), sub.triOrder.begin(), sub.triOrder.end());
+        res.maxDepth = std::max(res.maxDepth, sub.maxDepth);
+        return nodeBase;
     }
 
     // chooses a partition of ids_[first,last) and returns the split position
@@ -166,9 +190,11 @@ private:
         return m;
     }
 
-    void splitInto(int nodeIndex, int first, int last, int depth)
+    // ids_[first,last) are disjoint per subtree and boxes_ / cent_ are read-only, so the two halves of a large node are
+    // built concurrently near the root, each into its own Result
+    void splitInto(Result& res, int nodeIndex, int first, int last, int depth)
     {
-        res_.maxDepth = std::max(res_.maxDepth, depth);
+        res.maxDepth = std::max(res.maxDepth, depth);
         const int n = last - first;
         int m;
         if (n <= 1) m = last;            // single triangle: second child stays empty
@@ -176,19 +202,30 @@ private:
         const int ranges[2][2] = { { first, m }, { m, last } };
         int children[2];
         Box cbox[2];
-        for (int c = 0; c < 2; ++c) {
-            const int f = ranges[c][0], l = ranges[c][1];
-            if (l - f <= 0) { children[c] = ~0; cbox[c] = Box(); continue; }
-            cbox[c] = rangeBox(f, l);
-            if (l - f <= maxLeaf_) {
-                children[c] = makeLeaf(f, l);
-            } else {
-                children[c] = (int)res_.nodes.size();
-                res_.nodes.emplace_back();
-                splitInto(children[c], f, l, depth + 1);
+        const bool fork = parallel_ && depth <= 3 && n > 30000 && m - first > maxLeaf_ && last - m > maxLeaf_;
+        if (fork) {
+            Result sub[2];
+            for (int c = 0; c < 2; ++c) { cbox[c] = rangeBox(ranges[c][0], ranges[c][1]); sub[c].nodes.emplace_back(); }
+            auto job = std::async(std::launch::async, [&]() { splitInto(sub[0], 0, ranges[0][0], ranges[0][1], depth + 1); });
+            splitInto(sub[1], 0, ranges[1][0], ranges[1][1], depth + 1);
+            job.get();
+            children[0] = append(res, sub[0]);
+            children[1] = append(res, sub[1]);
+        } else {
+            for (int c = 0; c < 2; ++c) {
+                const int f = ranges[c][0], l = ranges[c][1];
+                if (l - f <= 0) { children[c] = ~0; cbox[c] = Box(); continue; }
+                cbox[c] = rangeBox(f, l);
+                if (l - f <= maxLeaf_) {
+                    children[c] = makeLeaf(res, f, l);
+                } else {
+                    children[c] = (int)res.nodes.size();
+                    res.nodes.emplace_back();
+                    splitInto(res, children[c], f, l, depth + 1);
+                }
             }
         }
-        Node& nd = res_.nodes[nodeIndex];
+        Node& nd = res.nodes[nodeIndex];
         std::memcpy(nd.c0lo, cbox[0].lo, 12); std::memcpy(nd.c0hi, cbox[0].hi, 12);
         std::memcpy(nd.c1lo, cbox[1].lo, 12); std::memcpy(nd.c1hi, cbox[1].hi, 12);
         nd.child0 = children[0];

@@ -7,9 +7,12 @@
 #include "objects.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <limits>
 
 #include "../../../include/rtb.h"
@@ -74,6 +77,7 @@ Triangle makeTriangle(const Vec3f& a, const Vec3f& b, const Vec3f& c, const Vec3
 
 bool Mesh::loadOBJ(const std::string& filename, const Options& opts)
 {
+    const auto tStart = std::chrono::steady_clock::now();
     const Matrix44f rMatrix = Matrix44f::rotationDeg(rot);
 
     std::ifstream in(filename, std::ios::in);
@@ -95,14 +99,21 @@ bool Mesh::loadOBJ(const std::string& filename, const Options& opts)
     auto tex = [&](size_t i) -> const Vec2f& { return uvs.at(i - 1); };
 
     std::string line;
+    std::vector<size_t> vi, ti, ni;   // per-face index lists, reused
     do {
         std::getline(in, line);
         const size_t hash = line.find('#');
         if (hash != std::string::npos) line.erase(hash);
         if (line.empty()) continue;
 
+        // first whitespace-delimited token, at most 31 characters (the reference reads it with sscanf("%s"), objects.cpp:241-251)
         char tag[32] = { 0 };
-        sscanf(line.c_str(), "%31s", tag);
+        {
+            const char* c = line.c_str();
+            while (*c == ' ' || *c == '\t' || *c == '\r' || *c == '\n' || *c == '\v' || *c == '\f') ++c;
+            size_t n = 0;
+            while (*c && !(*c == ' ' || *c == '\t' || *c == '\r' || *c == '\n' || *c == '\v' || *c == '\f') && n < 31) tag[n++] = *c++;
+        }
         const size_t skip = strlen(tag) + 1;
         const char* body = line.c_str() + std::min(skip, line.size());
 
@@ -163,13 +174,12 @@ bool Mesh::loadOBJ(const std::string& filename, const Options& opts)
             int slashes = 0;
             for (const char* p = body; *p; ++p) slashes += (*p == '/');
             const char* p = body;
+            vi.clear(); ti.clear(); ni.clear();
             if (slashes == 0) {
-                std::vector<size_t> vi;
                 for (size_t v; (v = nextIndex(p)) > 0;) vi.push_back(v);
                 for (size_t i = 1; i + 1 < vi.size(); ++i)
                     allTris.push_back(makeTriangle(vtx(vi[0]), vtx(vi[i]), vtx(vi[i + 1])));
             } else if (slashes % 2 == 0) {
-                std::vector<size_t> vi, ti, ni;
                 for (size_t v; (v = nextIndex(p)) > 0;) {
                     const size_t t = nextIndex(p);
                     const size_t n = nextIndex(p);
@@ -194,7 +204,14 @@ bool Mesh::loadOBJ(const std::string& filename, const Options& opts)
         }
     } while (in.good());
 
+    const auto tParsed = std::chrono::steady_clock::now();
     ac->setup(allTris, opts);
+    if (options::enableOutput) {   // the reference times this phase with a Timer("OBJ loading") (objects.cpp:217)
+        const auto tDone = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return (long long)std::chrono::duration_cast<std::chrono::milliseconds>(b - a).count(); };
+        printf("%-18s%lld ms\n", "OBJ loading", ms(tStart, tDone));
+        if (getenv("RTB_HOST_TIMING")) printf("  parse %lld ms, tree %lld ms, %zu triangles\n", ms(tStart, tParsed), ms(tParsed, tDone), allTris.size());
+    }
     return true;
 }
 
@@ -247,16 +264,33 @@ float AccelerationStructure::binarySearchSAH(int axis, const std::vector<Triangl
 
 void AccelerationStructure::setup(const std::vector<Triangle>& tris, const Options& opts)
 {
-    nodes.clear();
-    refs.clear();
     std::vector<int> ids(tris.size());
     for (size_t i = 0; i < ids.size(); ++i) ids[i] = (int)i;
-    build(tris, ids, rootBounds, 1, opts);
+    Subtree tree;
+    build(tree, tris, ids, rootBounds, 1, opts);
+    nodes.swap(tree.nodes);
+    refs.swap(tree.refs);
 }
 
-void AccelerationStructure::build(const std::vector<Triangle>& tris, std::vector<int>& ids, const Vec3f bounds[2], int depth,
+// appends a subtree built on its own (another thread), shifting its links into `out`'s coordinates
+void AccelerationStructure::append(Subtree& out, const Subtree& child)
+{
+    const int nodeBase = (int)out.nodes.size(), refBase = (int)out.refs.size();
+    for (Node n : child.nodes) {
+        if (n.right >= 0) n.right += nodeBase;
+        else n.firstRef += refBase;
+        out.nodes.push_back(n);
+    }
+    out.refs.insert(out.refs.end(), child.refs.begin(), child.refs.end());
+}
+
+// The two halves of a node are independent, so near the root they are built concurrently, each into its own Subtree,
+// and concatenated in the reference's order (self, low subtree, high subtree): the result is the sequential one bit for bit.
+void AccelerationStructure::build(Subtree& out, const std::vector<Triangle>& tris, std::vector<int>& ids, const Vec3f bounds[2], int depth,
     const Options& opts)
 {
+    std::vector<Node>& nodes = out.nodes;
+    std::vector<int>& refs = out.refs;
     const int self = (int)nodes.size();
     nodes.emplace_back();
     nodes[self].bounds[0] = bounds[0];
@@ -295,7 +329,18 @@ void AccelerationStructure::build(const std::vector<Triangle>& tris, std::vector
     highBox[0][axis] = split;
 
     std::vector<int>().swap(ids);   // release before recursing: the dragon's tree is 25 deep
-    build(tris, low, lowBox, depth + 1, opts);
+    const bool fork = depth <= 3 && low.size() + high.size() > 50000;
+    if (!fork) {
+        build(out, tris, low, lowBox, depth + 1, opts);
+        nodes[self].right = (int)nodes.size();
+        build(out, tris, high, highBox, depth + 1, opts);
+        return;
+    }
+    Subtree lowTree, highTree;
+    auto lowJob = std::async(std::launch::async, [&]() { build(lowTree, tris, low, lowBox, depth + 1, opts); });
+    build(highTree, tris, high, highBox, depth + 1, opts);
+    lowJob.get();
+    append(out, lowTree);
     nodes[self].right = (int)nodes.size();
-    build(tris, high, highBox, depth + 1, opts);
+    append(out, highTree);
 }

@@ -75,8 +75,11 @@ public:
     std::vector<int> refs;
 
 private:
-    void build(const std::vector<Triangle>& tris, std::vector<int>& ids, const Vec3f bounds[2], int depth,
+    // a subtree in its own coordinates: node links and reference ranges are relative to its first node / first ref
+    struct Subtree { std::vector<Node> nodes; std::vector<int> refs; };
+    static void build(Subtree& out, const std::vector<Triangle>& tris, std::vector<int>& ids, const Vec3f bounds[2], int depth,
         const Options& options);
+    static void append(Subtree& out, const Subtree& child);
 };
 
 struct TextureRGB8 {

@@ -40,6 +40,8 @@ def shim():
         lib.shim_render.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         lib.shim_render_fast.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         lib.shim_primary_rect.argtypes = [C.POINTER(_ffi.RtbScene), C.POINTER(C.c_int)]
+        lib.shim_bvh_digest.argtypes = [C.POINTER(_ffi.RtbScene), C.c_int, C.c_int]
+        lib.shim_bvh_digest.restype = C.c_uint64
         _shim = lib
     return _shim
 

@@ -165,6 +165,21 @@ int shim_render(const RtbScene* s, float* pass1, float* final, unsigned long lon
 // same, but meshes are searched through the fast path (search BVH + eligibility tables)
 int shim_render_fast(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4]) { return render_impl(s, pass1, final, counters, true); }
 
+// FNV-1a digest of a mesh's search BVH (nodes + leaf-ordered triangles); serial != 0 forces the single-threaded build
+unsigned long long shim_bvh_digest(const RtbScene* s, int mesh, int serial)
+{
+    if (serial) setenv("RTB_BVH_SERIAL", "1", 1); else unsetenv("RTB_BVH_SERIAL");
+    rtpack::FastPath fp;
+    rtpack::packFastPath(s->meshes[mesh], fp);
+    unsetenv("RTB_BVH_SERIAL");
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* c = static_cast<const unsigned char*>(p); for (size_t i = 0; i < n; ++i) { h ^= c[i]; h *= 1099511628211ull; } };
+    mix(fp.nodes.data(), fp.nodes.size() * sizeof(rtbvh::Node));
+    mix(fp.tris.data(), fp.tris.size() * sizeof(float4));
+    mix(&fp.maxDepth, sizeof fp.maxDepth);
+    return h;
+}
+
 // the pixel rectangle primary rays are limited to (scene_pack.h primaryRect), computed exactly like rtb_create does
 int shim_primary_rect(const RtbScene* s, int rect[4])
 {

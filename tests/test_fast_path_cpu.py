@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import rendering_b200 as rb
-from helpers import HAVE_ASSETS, MULTI_MESH_SCENE, diff_stats, golden_case, load, needs_assets, oracle_render, shim_primary_rect, shim_render, GOLDEN
+from helpers import shim, HAVE_ASSETS, MULTI_MESH_SCENE, diff_stats, golden_case, load, needs_assets, oracle_render, shim_primary_rect, shim_render, GOLDEN
 
 
 @pytest.mark.parametrize("name", ["cfg2_128", "cfg4_240", "cfgD_160"])
@@ -106,3 +106,18 @@ def test_several_meshes_with_every_material_on_the_cpu():
     d = diff_stats(bfin, ofin)
     assert d["rms"] <= 1e-4 and d["max_abs"] <= 2.5e-7, d
     _check_rect(sc)
+
+
+def test_concurrent_builds_reproduce_the_sequential_trees():
+    """Both tree builders fork near the root (host reference tree: std::async per half; search BVH likewise) and must
+    lay the result out exactly like the sequential recursion."""
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    sc = rb.Scene(rb.scene_path("cfgD_dragon_1080"))          # 249 999 triangles: large enough to fork
+    # reference tree: node / leaf / reference counts of the unmodified reference (SURVEY.md Appendix B)
+    st = sc.tree_stats(0)
+    assert (st["nodes"], st["leaves"], st["refs"], st["maxLeaf"], st["maxDepth"]) == (48407, 24204, 514317, 15756, 25)
+    a = shim().shim_bvh_digest(sc.view, 0, 1)
+    b = shim().shim_bvh_digest(sc.view, 0, 0)
+    c = shim().shim_bvh_digest(sc.view, 0, 0)
+    assert a == b == c
