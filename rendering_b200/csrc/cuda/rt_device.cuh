@@ -447,15 +447,178 @@ RT_HD float fresnel(V3 dir, V3 n, float ior)   // scene.cpp:698-722
     return (rs * rs + rp * rp) / 2;
 }
 
-// std::pow(float,float) == glibc powf, which is correctly rounded in all but vanishingly rare
-// cases; CUDA's powf is only good to a few ulp, so evaluate in double and round once.
-RT_HD float powExact(float x, float y) { return (float)pow((double)x, (double)y); }
-
 #if defined(__CUDA_ARCH__)
 #define RT_LDG(p) __ldg(p)
 #else
 #define RT_LDG(p) (*(p))
 #endif
+// ------------------------------------------------------------------------------------------------
+// powf, bit for bit
+// ------------------------------------------------------------------------------------------------
+// The reference's std::pow(float, float) (scene.cpp:824,846,867,887,917,937; :565) is glibc's powf, a THIRD-PARTY
+// routine absent from /root/reference: glibc 2.39 (Ubuntu 24.04, the image both boxes run), sysdeps/ieee754/flt-32/
+// e_powf.c + e_powf_log2_data.c + math/e_exp2f_data.c (Szabolcs Nagy's algorithm from ARM optimized-routines).
+// It is NOT correctly rounded (0.82 ULP: log2(x) from a 16-entry table and a degree-5 polynomial, 2^(y log2 x) from a
+// 32-entry table and a cubic, all in double), so a correctly rounded pow differs from it by one ulp on ~0.1 % of
+// inputs.  This is a restatement of the published algorithm with the table constants of that glibc build and the
+// operation grouping of the variant x86-64 selects on CPUs with FMA (__powf_fma: every a*b+c below is one fused
+// operation — read off the library's disassembly; tests/test_powf.py pins it against the host's powf on millions of inputs).
+#define RT_POWF_LOG2_TAB { \
+    0x3ff661ec79f8f3beULL, 0xbfdefec65b963019ULL, 0x3ff571ed4aaf883dULL, 0xbfdb0b6832d4fca4ULL, \
+    0x3ff49539f0f010b0ULL, 0xbfd7418b0a1fb77bULL, 0x3ff3c995b0b80385ULL, 0xbfd39de91a6dcf7bULL, \
+    0x3ff30d190c8864a5ULL, 0xbfd01d9bf3f2b631ULL, 0x3ff25e227b0b8ea0ULL, 0xbfc97c1d1b3b7af0ULL, \
+    0x3ff1bb4a4a1a343fULL, 0xbfc2f9e393af3c9fULL, 0x3ff12358f08ae5baULL, 0xbfb960cbbf788d5cULL, \
+    0x3ff0953f419900a7ULL, 0xbfaa6f9db6475fceULL, 0x3ff0000000000000ULL, 0x0000000000000000ULL, \
+    0x3fee608cfd9a47acULL, 0x3fb338ca9f24f53dULL, 0x3feca4b31f026aa0ULL, 0x3fc476a9543891baULL, \
+    0x3feb2036576afce6ULL, 0x3fce840b4ac4e4d2ULL, 0x3fe9c2d163a1aa2dULL, 0x3fd40645f0c6651cULL, \
+    0x3fe886e6037841edULL, 0x3fd88e9c2c1b9ff8ULL, 0x3fe767dcf5534862ULL, 0x3fdce0a44eb17bccULL }
+#define RT_EXP2F_TAB { \
+    0x3ff0000000000000ULL, 0x3fefd9b0d3158574ULL, 0x3fefb5586cf9890fULL, 0x3fef9301d0125b51ULL, \
+    0x3fef72b83c7d517bULL, 0x3fef54873168b9aaULL, 0x3fef387a6e756238ULL, 0x3fef1e9df51fdee1ULL, \
+    0x3fef06fe0a31b715ULL, 0x3feef1a7373aa9cbULL, 0x3feedea64c123422ULL, 0x3feece086061892dULL, \
+    0x3feebfdad5362a27ULL, 0x3feeb42b569d4f82ULL, 0x3feeab07dd485429ULL, 0x3feea47eb03a5585ULL, \
+    0x3feea09e667f3bcdULL, 0x3fee9f75e8ec5f74ULL, 0x3feea11473eb0187ULL, 0x3feea589994cce13ULL, \
+    0x3feeace5422aa0dbULL, 0x3feeb737b0cdc5e5ULL, 0x3feec49182a3f090ULL, 0x3feed503b23e255dULL, \
+    0x3feee89f995ad3adULL, 0x3feeff76f2fb5e47ULL, 0x3fef199bdd85529cULL, 0x3fef3720dcef9069ULL, \
+    0x3fef5818dcfba487ULL, 0x3fef7c97337b9b5fULL, 0x3fefa4afa2a490daULL, 0x3fefd0765b6e4540ULL }
+static const unsigned long long kPowfLog2TabHost[32] = RT_POWF_LOG2_TAB;   // (invc, logc) pairs
+static const unsigned long long kExp2fTabHost[32] = RT_EXP2F_TAB;
+#if defined(__CUDACC__)
+static __device__ const unsigned long long kPowfLog2TabDev[32] = RT_POWF_LOG2_TAB;
+static __device__ const unsigned long long kExp2fTabDev[32] = RT_EXP2F_TAB;
+#endif
+
+RT_HD double bitsToDouble(unsigned long long u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    union { unsigned long long u; double d; } c; c.u = u; return c.d;
+#endif
+}
+RT_HD unsigned long long doubleBits(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(d);
+#else
+    union { double d; unsigned long long u; } c; c.d = d; return c.u;
+#endif
+}
+RT_HD uint32_t floatBitsU(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+// single IEEE operations, immune to contraction / re-association by either compiler
+#if defined(__CUDA_ARCH__)
+RT_HD double dFma(double a, double b, double c) { return __fma_rn(a, b, c); }
+RT_HD double dMul(double a, double b) { return __dmul_rn(a, b); }
+RT_HD double dAdd(double a, double b) { return __dadd_rn(a, b); }
+#else
+RT_HD double dFma(double a, double b, double c) { return fma(a, b, c); }
+RT_HD double dMul(double a, double b) { return a * b; }
+RT_HD double dAdd(double a, double b) { return a + b; }
+#endif
+
+// e_powf.c checkint(): 0 = y is not an integer, 1 = odd integer, 2 = even integer
+RT_HD int powfCheckInt(uint32_t iy)
+{
+    const int e = (int)((iy >> 23) & 0xff);
+    if (e < 0x7f) return 0;
+    if (e > 0x7f + 23) return 2;
+    if (iy & ((1u << (0x7f + 23 - e)) - 1)) return 0;
+    if (iy & (1u << (0x7f + 23 - e))) return 1;
+    return 2;
+}
+
+RT_HD float powfGlibc(float x, float y)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned long long* logTab = kPowfLog2TabDev;
+    const unsigned long long* expTab = kExp2fTabDev;
+#else
+    const unsigned long long* logTab = kPowfLog2TabHost;
+    const unsigned long long* expTab = kExp2fTabHost;
+#endif
+    unsigned long long signBias = 0;
+    uint32_t ix = floatBitsU(x);
+    const uint32_t iy = floatBitsU(y);
+    const bool yZeroInfNan = 2 * iy - 1 >= 2u * 0x7f800000u - 1;
+    if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u || yZeroInfNan) {
+        // x is subnormal, zero, negative, inf or nan — or y is zero, inf or nan
+        if (yZeroInfNan) {
+            if (2 * iy == 0) return (2 * (ix ^ 0x00400000u) > 2u * 0x7fc00000u) ? x + y : 1.0f;        // signalling NaN ^ 0
+            if (ix == 0x3f800000u) return (2 * (iy ^ 0x00400000u) > 2u * 0x7fc00000u) ? x + y : 1.0f;
+            if (2 * ix > 2u * 0x7f800000u || 2 * iy > 2u * 0x7f800000u) return x + y;
+            if (2 * ix == 2 * 0x3f800000u) return 1.0f;
+            if ((2 * ix < 2 * 0x3f800000u) == !(iy & 0x80000000u)) return 0.0f;   // |x| < 1 && y == inf, |x| > 1 && y == -inf
+            return y * y;
+        }
+        if (2 * ix - 1 >= 2u * 0x7f800000u - 1) {   // x is zero, inf or nan
+            float x2 = x * x;
+            if ((ix & 0x80000000u) && powfCheckInt(iy) == 1) x2 = -x2;
+            return (iy & 0x80000000u) ? 1 / x2 : x2;
+        }
+        if (ix & 0x80000000u) {   // finite x < 0
+            const int yint = powfCheckInt(iy);
+            if (yint == 0) return (x - x) / (x - x);
+            if (yint == 1) signBias = 1ull << (5 + 11);   // SIGN_BIAS = 1 << (EXP2F_TABLE_BITS + 11)
+            ix &= 0x7fffffffu;
+        }
+        if (ix < 0x00800000u) {   // subnormal x: normalise so the exponent becomes negative
+            ix = floatBitsU(bitsToFloat(ix) * 8388608.0f);
+            ix &= 0x7fffffffu;
+            ix -= 23u << 23;
+        }
+    }
+    // log2_inline: x = 2^k z, z in [OFF, 2 OFF); log2(x) = k + log2(c) + log2(z / c) with c near the centre of z's sub-interval
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (int)((tmp >> (23 - 4)) % 16);
+    const uint32_t top = tmp & 0xff800000u;
+    const uint32_t iz = ix - top;
+    const int k = (int)top >> 23;   // arithmetic shift
+    const double invc = bitsToDouble(RT_LDG(logTab + 2 * i)), logc = bitsToDouble(RT_LDG(logTab + 2 * i + 1));
+    const double z = (double)bitsToFloat(iz);
+    const double A0 = bitsToDouble(0x3fd27616c9496e0bULL), A1 = bitsToDouble(0xbfd71969a075c67aULL), A2 = bitsToDouble(0x3fdec70a6ca7baddULL),
+                 A3 = bitsToDouble(0xbfe7154748bef6c8ULL), A4 = bitsToDouble(0x3ff71547652ab82bULL);
+    const double r = dFma(z, invc, -1.0);
+    const double y0 = dAdd(logc, (double)k);
+    const double r2 = dMul(r, r);
+    const double yy = dFma(A0, r, A1);
+    const double p = dFma(A2, r, A3);
+    const double r4 = dMul(r2, r2);
+    double q = dFma(A4, r, y0);
+    q = dFma(p, r2, q);
+    const double logx = dFma(yy, r4, q);
+    const double ylogx = dMul((double)y, logx);   // cannot overflow: y is single precision
+    if (((doubleBits(ylogx) >> 47) & 0xffff) >= (0x405f800000000000ULL >> 47)) {   // |y log2 x| >= 126
+        const float sgn = signBias ? -1.0f : 1.0f;
+        if (ylogx > bitsToDouble(0x405fffffffd1d571ULL)) return sgn * bitsToFloat(0x7f800000u);   // > 0x1.fffffffd1d571p+6: overflow
+        if (ylogx <= -150.0) return sgn * 0.0f;                                                              // underflow
+        if (ylogx < -149.0) return sgn * bitsToFloat(1u);   // __math_may_uflowf: 0x1.4p-75f squared, rounded to nearest
+    }
+    // exp2_inline: 2^x = 2^(k/32) 2^r with r in [-1/64, 1/64]
+    const double shift = bitsToDouble(0x42e8000000000000ULL);   // 0x1.8p+52 / 32
+    double kd = dAdd(ylogx, shift);
+    const unsigned long long ki = doubleBits(kd);
+    kd = dAdd(kd, -shift);
+    const double rr = dAdd(ylogx, -kd);
+    unsigned long long t = RT_LDG(expTab + (ki % 32));
+    t += (ki + signBias) << (52 - 5);
+    const double s = bitsToDouble(t);
+    const double C0 = bitsToDouble(0x3fac6af84b912394ULL), C1 = bitsToDouble(0x3fcebfce50fac4f3ULL), C2 = bitsToDouble(0x3fe62e42ff0c52d6ULL);
+    const double zz = dFma(C0, rr, C1);
+    const double rr2 = dMul(rr, rr);
+    double e = dFma(C2, rr, 1.0);
+    e = dFma(zz, rr2, e);
+    e = dMul(e, s);
+    return (float)e;
+}
+RT_HD float powExact(float x, float y) { return powfGlibc(x, y); }
+
 RT_HD int floatBits(float f)
 {
 #if defined(__CUDA_ARCH__)
@@ -514,7 +677,7 @@ template <bool ANY>
 RT_HD bool walkMeshFast(const Scene& sc, const Mesh& me, const RayCtx& r, int* stack, int stackStride, float tLimit,
     float& tBest, float& uBest, float& vBest, int& triBest)
 {
-    if (me.nNodes == 0) return false;
+    if (me.nNodes == 0 || me.nTris == 0) return false;
     const bool cull = sc.flags & FLAG_CULL;
     bool found = false;
     int slotBest = 0x7fffffff;

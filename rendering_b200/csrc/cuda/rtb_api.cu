@@ -715,7 +715,9 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             d.nNodes = m.nNodes; d.nSlots = m.nRefs; d.nTris = m.nTris; d.maxDepth = pm.maxDepth;
             h->refTreeDepth.push_back(pm.maxDepth);
             if (createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK)) h->stackEntries = std::max(h->stackEntries, pm.maxDepth + 1);
-            if (m.nNodes > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
+            // a mesh whose .obj yields no usable face still has a one-node tree (objects.cpp:389): nothing to search, the
+            // kernels skip it (bvhTris stays null)
+            if (m.nNodes > 0 && m.nTris > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
             meshes.push_back(d);
         }
         for (int i = 0; i < s->nObjects; ++i) rtpack::objectBounds(s->objects[i], h->geomBounds, h->unbounded);

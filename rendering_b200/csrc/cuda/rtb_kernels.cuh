@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                             obj++;
                         } else if (ob.type == OBJ_MESH) {
                             me = &sc.meshes[ob.mesh];
-                            if (me->nNodes == 0) obj++;
+                            if (me->nNodes == 0 || me->nTris == 0) obj++;   // missing .obj / no usable face: nothing to hit
                             else { cur = 0; sp = 0; found = false; slotBest = 0x7fffffff; tM = tNear; }
                         } else {
                             float t = FLT_MAX;
@@ -892,13 +892,12 @@ __global__ void __launch_bounds__(kBlock) k_sobel(int width, int height, const f
         if (interior) {
             // val = sqrtf(powf(|Gx|,2) + powf(|Gy|,2)) > 0.5f with |G| = (float)sqrt((double)G.G)  (scene.cpp:565-566,
             // geometry.h:99).  Away from the threshold the float sum of squares decides with a wide margin and the
-            // double-precision square roots are skipped; powf(v, 2) is v*v to within glibc's rounding.
+            // double-precision square roots and the two powf evaluations are skipped.
             const float s2 = dot(gx, gx) + dot(gy, gy);
             if (s2 > 0.2501f) flag = true;
             else if (s2 < 0.2499f) flag = false;
             else {
-                const float lx = length(gx), ly = length(gy);
-                flag = sqrtf(lx * lx + ly * ly) > 0.5f;
+                flag = sqrtf(powExact(length(gx), 2.0f) + powExact(length(gy), 2.0f)) > 0.5f;
             }
             pix = y * width + x;
         }

@@ -5,6 +5,7 @@
 // lights, Fresnel, skybox) can be checked bit-for-bit against the reference on the CPU box, where
 // no GPU exists.  It is NOT part of the product and NOT the oracle: nothing under rendering_b200/
 // links it, and the wavefront plumbing of the kernels is exercised only by the -m gpu tests.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -178,6 +179,18 @@ unsigned long long shim_bvh_digest(const RtbScene* s, int mesh, int serial)
     mix(fp.tris.data(), fp.tris.size() * sizeof(float4));
     mix(&fp.maxDepth, sizeof fp.maxDepth);
     return h;
+}
+
+// rt_device.cuh's restatement of glibc powf over n (x, y) pairs
+void shim_powf(const float* x, const float* y, int n, float* out)
+{
+    for (int i = 0; i < n; ++i) out[i] = rt::powfGlibc(x[i], y[i]);
+}
+
+// the C library's own powf over the same pairs (what the reference's std::pow(float, float) resolves to)
+void shim_libm_powf(const float* x, const float* y, int n, float* out)
+{
+    for (int i = 0; i < n; ++i) { volatile float a = x[i], b = y[i]; out[i] = powf(a, b); }
 }
 
 // the pixel rectangle primary rays are limited to (scene_pack.h primaryRect), computed exactly like rtb_create does

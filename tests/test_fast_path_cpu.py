@@ -121,3 +121,18 @@ def test_concurrent_builds_reproduce_the_sequential_trees():
     b = shim().shim_bvh_digest(sc.view, 0, 0)
     c = shim().shim_bvh_digest(sc.view, 0, 0)
     assert a == b == c
+
+
+@pytest.mark.parametrize("obj,body", [("only_vertices.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\n"),
+                                      ("odd_slashes.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nf 1/1 2/2 3/3\n"),
+                                      ("one_triangle.obj", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")])
+def test_mesh_without_usable_faces_is_skipped_by_the_fast_path(tmp_path, obj, body):
+    # a file that exists but yields no face gives a one-node tree over zero triangles (objects.cpp:376-389)
+    (tmp_path / obj).write_text(body)
+    text = ("[options]\nwidth=48\nheight=40\nbackground_color=0.2,0.3,0.4\n[light]\ntype=point\nposition=0,2,0\n"
+            f"[object]\ntype=mesh\npos=0,0,-3\nsize=2,2,2\nname={obj}\n[object]\ntype=sphere\npos=0.5,0,-4\nradius=1\n[end]\n")
+    sc = rb.Scene(text=text, asset_dir=str(tmp_path))
+    _, ofin, ocnt = oracle_render(sc)
+    for fast in (False, True):
+        _, fin, cnt = shim_render(sc, fast=fast)
+        assert np.array_equal(fin.view(np.uint32), ofin.view(np.uint32)) and cnt["rays"] == ocnt["rays"]

@@ -194,6 +194,28 @@ def test_degenerate_scenes():
         check_against_oracle(rb.Scene(text=text), exact=True)
 
 
+FACELESS_OBJS = {"only_vertices.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\n",
+                 # 'f v/vt v/vt v/vt' has an odd slash count: "Unhandled slash count", the face is dropped (objects.cpp:376-378)
+                 "odd_slashes.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 0 1\nf 1/1 2/2 3/3\n",
+                 "one_triangle.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n"}
+
+
+@pytest.mark.parametrize("obj", sorted(FACELESS_OBJS))
+def test_mesh_whose_obj_yields_no_usable_face(tmp_path, obj):
+    # the file exists, so the loader builds a one-node tree, but there is nothing (or a single triangle) to search: the
+    # fast path must skip the mesh like the reference's walk over an empty leaf does, not dereference a null triangle array
+    (tmp_path / obj).write_text(FACELESS_OBJS[obj])
+    text = ("[options]\nwidth=48\nheight=40\nbackground_color=0.2,0.3,0.4\n[light]\ntype=point\nposition=0,2,0\n"
+            f"[object]\ntype=mesh\npos=0,0,-3\nsize=2,2,2\nname={obj}\n[object]\ntype=sphere\npos=0.5,0,-4\nradius=1\n[end]\n")
+    sc = rb.Scene(text=text, asset_dir=str(tmp_path))
+    check_against_oracle(sc, exact=True)
+    rng = np.random.default_rng(5)
+    rays = np.concatenate([np.zeros((2000, 3), np.float32), (rng.normal(size=(2000, 3)) * [0.3, 0.3, 0.1] + [0, 0, -1]).astype(np.float32)], 1)
+    tuv, ot = rb.Renderer(sc).trace(rays)
+    otuv, oot = oracle_trace(sc, rays)
+    assert np.array_equal(ot, oot) and np.array_equal(tuv.view(np.uint32)[ot[:, 0] >= 0], otuv.view(np.uint32)[oot[:, 0] >= 0])
+
+
 def test_row_ranges_and_strips_reassemble_to_the_full_frame():
     sc = rb.Scene(text=MIXED_SCENE.replace("width=96", "width=120").replace("height=64", "height=77"))
     r = rb.Renderer(sc)
