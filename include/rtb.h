@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RTB_ABI_VERSION 1
+#define RTB_ABI_VERSION 2
 
 /* ---- status codes (reference: LOG_ERROR() prints and exit(-1)s, include/util.h:13-19) ---- */
 #define RTB_OK             0
@@ -137,7 +137,10 @@ typedef struct RtbScene {
 
 /* kernel kinds for RtbStats.msKernel / launchesKernel */
 enum { RTB_K_RAYGEN = 0, RTB_K_TRACE = 1, RTB_K_SURFACE = 2, RTB_K_SHADOW = 3, RTB_K_SHADE = 4, RTB_K_COMBINE = 5,
-       RTB_K_SOBEL = 6, RTB_K_OUTPUT = 7, RTB_NKINDS = 8 };
+       RTB_K_SOBEL = 6, RTB_K_OUTPUT = 7,
+       RTB_K_TILE = 8,        /* the tile pipeline's fused kernel, pass 1 (all recursion levels of every tile)   */
+       RTB_K_TILE_SSAA = 9,   /* the same kernel over the 4 samples of the flagged pixels, incl. their mean      */
+       RTB_NKINDS = 10 };
 
 /* Work counters of one rtb_render call (64-bit: the reference's are int and wrap, stats.h:11-16). */
 typedef struct RtbStats {
@@ -149,6 +152,8 @@ typedef struct RtbStats {
     uint64_t h2dBytes, d2hBytes;                  /* host<->device bytes copied inside the call    */
     uint64_t shadowRaysSkipped;   /* shadow rays (counted in `rays`) whose visibility cannot affect the pixel
                                      and that the fast path therefore does not trace                      */
+    uint64_t backgroundPixels;    /* primary rays (counted in `rays`) that lie outside the screen-space bounds of the
+                                     geometry and are resolved by the background pre-fill instead of a traversal     */
     uint32_t kernelLaunches;
     uint32_t levels;
     float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */
@@ -192,6 +197,8 @@ const char* rtb_host_last_error(void);
 #define RTB_CREATE_COUNTERS  (1u << 0)   /* count box / triangle tests (slower; parity of work)   */
 #define RTB_CREATE_EXACT_WALK (1u << 1)  /* traverse exactly like objects.cpp:587-631 (no culling) */
 #define RTB_CREATE_WALK_STATS (1u << 3)  /* fill RtbStats.walkNodes / walkTris / walkEligibility (slower kernels)    */
+#define RTB_CREATE_WAVEFRONT (1u << 4)   /* frame-wide level pipeline (one launch per stage and recursion level) instead of
+                                            the default tile pipeline (whole recursion per tile inside one kernel); same bits */
 #define RTB_CREATE_KERNEL_TIMING (1u << 2) /* fill RtbStats.msKernel: CUDA events around every launch (costs ~6 us
                                               of stream time per launch, so it is off by default)               */
 

@@ -20,6 +20,7 @@
 
 #include "../../../include/rtb.h"
 #include "rtb_kernels.cuh"
+#include "rtb_tile.cuh"
 #include "scene_pack.h"
 
 namespace {
@@ -96,6 +97,21 @@ struct RtbHandle {
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
     int walkBlocksPerSm[4] = { 1, 1, 1, 1 };   // resident CTAs per SM of k_walk<false, GEN 0..2> / k_walk<true> with that stack
+
+    // tile pipeline (rtb_tile.cuh): per-group scratch slabs and their capacities (grown after an overflow, never shrunk)
+    bool tilePipeline = true;
+    DevBuf tileSlab;
+    int tileCapRays = 0, tileCapInterior = 0;
+    int tileBlocksPerSm[3] = { 0, 0, 0 };   // resident CTAs per SM of k_tile<GEN 0..2> for this scene (0 = not queried yet)
+    // staged form (one 1024-thread CTA per SM, four groups, the top of one mesh's search BVH in shared memory)
+    bool tileStaged = false;
+    int stagedMeshIndex = -1;
+    const float4* stagedNodesSrc = nullptr;
+    const float4* stagedTrisSrc = nullptr;
+    int stagedNodesAll = 0, stagedTrisAll = 0;   // that mesh's node / triangle counts
+    int stagedNodes = 0, stagedTris = 0;         // what fits next to the stacks
+    size_t smemOptin = 0;
+    bool stagedAttrSet[3] = { false, false, false };
 
     QueueBufs rays[2];
     DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, userRays, outStage;
@@ -187,10 +203,15 @@ rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
 
 // Fast-path data of one mesh: search BVH over its unique triangles (bvh_build.h) and the tables that
 // let the kernel evaluate the reference tree's eligibility rule for a single triangle.
-int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d)
+int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d, int meshIndex)
 {
     rtpack::FastPath fp;
     rtpack::packFastPath(m, fp);
+    if ((int)fp.nodes.size() > h->stagedNodesAll) {   // the largest search BVH is the one worth keeping in shared memory
+        h->stagedMeshIndex = meshIndex;
+        h->stagedNodesAll = (int)fp.nodes.size();
+        h->stagedTrisAll = (int)(fp.tris.size() / 3);
+    }
     if (fp.maxDepth > rtk::kStackDepth) throw std::runtime_error("search BVH deeper than the traversal stack (64)");
     d.bvhNodes = reinterpret_cast<const float4*>(upload(h, fp.nodes.data(), fp.nodes.size()));
     d.bvhTris = upload(h, fp.tris.data(), fp.tris.size());
@@ -270,8 +291,17 @@ void resolveSpans(RtbHandle* h)
 // Sizes every per-frame buffer for: level-0 queues of up to n0 rays, deeper levels of up to nDeep rays,
 // nInterior interior records, nFlagged SSAA pixels on top of `framePixels` framebuffer slots.
 // Slot layout: [0, framePixels) framebuffer | [framePixels, +4*capFlagged) SSAA samples | 2 per interior record.
-void ensureCapacity(RtbHandle* h, cudaStream_t st, long long framePixels, long long n0, long long nDeep, long long nInterior, long long nFlagged)
+void ensureCapacity(RtbHandle* h, cudaStream_t st, long long framePixels, long long n0, long long nDeep, long long nInterior, long long nFlagged,
+    bool frameWideQueues = true)
 {
+    if (!frameWideQueues) {
+        // tile pipeline: queues live in the groups' scratch slabs (enqueueTile); only the framebuffer and the SSAA list are frame-sized
+        h->capFlagged = std::max(h->capFlagged, nFlagged);
+        h->flagged.reserve((size_t)std::max(1LL, h->capFlagged) * sizeof(int), st, false);
+        h->capSlots = std::max(h->capSlots, framePixels);
+        h->slots.reserve((size_t)h->capSlots * 3 * sizeof(float), st, false);
+        return;
+    }
     if (std::max(n0, nDeep) > (1LL << 28)) throw CudaError{ cudaErrorMemoryAllocation, "ray queue larger than 2^28 rays" };
     h->capLevel0 = std::max(h->capLevel0, n0);
     h->capDeep = std::max(h->capDeep, h->levels > 1 ? nDeep : 0LL);
@@ -290,8 +320,104 @@ void ensureCapacity(RtbHandle* h, cudaStream_t st, long long framePixels, long l
     h->vis.reserve((size_t)(nMax * S), st, false);
     h->interiors.reserve((size_t)std::max(1LL, h->capInterior) * sizeof(rtk::Interior), st, false);
     h->flagged.reserve((size_t)std::max(1LL, h->capFlagged) * sizeof(int), st, false);
-    h->capSlots = framePixels + 4 * h->capFlagged + 2 * h->capInterior;
+    h->capSlots = std::max(h->capSlots, framePixels + 4 * h->capFlagged + 2 * h->capInterior);
     h->slots.reserve((size_t)h->capSlots * 3 * sizeof(float), st, false);
+}
+
+// ---- tile pipeline ----------------------------------------------------------------------------------------------------
+constexpr int kStagedGroups = 4;   // groups of the staged kernel's single CTA per SM
+template <int GEN, bool DEEP, bool STATS>
+void launchTile(int grid, size_t smem, cudaStream_t st, const rt::Scene& sc, const rtk::TileArgs& a)
+{
+    rtk::k_tile<GEN, DEEP, STATS, 1><<<grid, rtk::kTileThreads, smem, st>>>(sc, a);
+}
+template <int GEN>
+void launchTileStaged(bool deep, bool& attrSet, size_t smemOptin, int grid, size_t smem, cudaStream_t st, const rt::Scene& sc, const rtk::TileArgs& a)
+{
+    if (!attrSet) {   // the attribute is per function, not per handle: always ask for the device's opt-in maximum
+        if (deep) CK(cudaFuncSetAttribute(rtk::k_tile<GEN, true, false, kStagedGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOptin));
+        else CK(cudaFuncSetAttribute(rtk::k_tile<GEN, false, false, kStagedGroups, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemOptin));
+        attrSet = true;
+    }
+    if (deep) rtk::k_tile<GEN, true, false, kStagedGroups, true><<<grid, rtk::kTileThreads * kStagedGroups, smem, st>>>(sc, a);
+    else rtk::k_tile<GEN, false, false, kStagedGroups, true><<<grid, rtk::kTileThreads * kStagedGroups, smem, st>>>(sc, a);
+}
+template <int GEN>
+void launchTileGen(bool deep, bool stats, int grid, size_t smem, cudaStream_t st, const rt::Scene& sc, const rtk::TileArgs& a)
+{
+    if (deep) { if (stats) launchTile<GEN, true, true>(grid, smem, st, sc, a); else launchTile<GEN, true, false>(grid, smem, st, sc, a); }
+    else { if (stats) launchTile<GEN, false, true>(grid, smem, st, sc, a); else launchTile<GEN, false, false>(grid, smem, st, sc, a); }
+}
+template <int GEN>
+int tileOccupancy(bool deep, size_t smem)
+{
+    int b = 0;
+    if (deep) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rtk::k_tile<GEN, true, false, 1>, rtk::kTileThreads, smem));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, rtk::k_tile<GEN, false, false, 1>, rtk::kTileThreads, smem));
+    return std::max(1, b);
+}
+
+size_t tileSmemBytes(const RtbHandle* h)
+{
+    return ((sizeof(rtk::TileShared) + 15) & ~(size_t)15) + (size_t)h->stackEntries * rtk::kTileThreads * sizeof(int);
+}
+
+// castRay for `total` level-0 rays (an upper bound when only the device knows the count), tile by tile, in one launch.
+void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk::GenArgs& gen, long long total, rtk::RayQueue userQ = rtk::RayQueue{},
+    int nUser = 0)
+{
+    const bool deep = h->levels > 1;
+    const bool stats = h->createFlags & RTB_CREATE_WALK_STATS;
+    const bool staged = h->tileStaged && !stats && h->stagedNodes > 0;
+    const size_t smem = staged ? rtk::tileSmemStagedOffset(kStagedGroups, h->stackEntries) + (size_t)h->stagedNodes * 64 + (size_t)h->stagedTris * 48
+                               : tileSmemBytes(h);
+    if (!staged && h->tileBlocksPerSm[genKind] == 0)
+        h->tileBlocksPerSm[genKind] = genKind == rtk::GEN_PRIMARY ? tileOccupancy<rtk::GEN_PRIMARY>(deep, smem)
+            : genKind == rtk::GEN_SSAA ? tileOccupancy<rtk::GEN_SSAA>(deep, smem) : tileOccupancy<rtk::GEN_QUEUE>(deep, smem);
+    const long long groups = staged ? (long long)h->smCount * kStagedGroups : (long long)h->smCount * h->tileBlocksPerSm[genKind];
+    // tile size: ONE 32-ray batch per warp of the group.  Measured on B200 (tools/gpu_sweep.sh, frame ms cfg1 / cfg3 / cfg4 /
+    // dragon): 256 rays 0.49 / 0.92 / 0.46 / 1.39, 512 rays 0.55 / 0.99 / 0.51 / 1.44, 1024 rays 0.67 / 1.15 / 0.62 / 1.64 —
+    // small tiles keep the groups of an SM out of phase and the dynamic tile cursor balances the SMs.
+    static const int forced = getenv("RTB_TILE_RAYS") ? atoi(getenv("RTB_TILE_RAYS")) : 0;
+    long long R = forced > 0 ? forced : rtk::kTileThreads;
+    R = std::max<long long>(rtk::kTileThreads, std::min(1024LL, R)) & ~31LL;
+    const int S = h->scene.shadowRaysPerHit;
+    h->tileCapRays = std::max<long long>(h->tileCapRays, deep ? 2 * R : R);
+    h->tileCapInterior = deep ? std::max<long long>(h->tileCapInterior, 4 * R) : 0;
+    const unsigned long long slab = rtk::tileSlabBytes(h->tileCapRays, h->tileCapInterior, 1024, S, h->levels);
+    h->tileSlab.reserve((size_t)(groups * slab), st, false);
+    const long long tiles = (total + R - 1) / R;
+    const int grid = staged ? (int)std::max(1LL, std::min<long long>(h->smCount, (tiles + kStagedGroups - 1) / kStagedGroups))
+                            : (int)std::max(1LL, std::min(groups, tiles));
+    rtk::TileArgs a{};
+    a.slab = h->tileSlab.as<char>();
+    a.slabBytes = slab;
+    a.capRays = h->tileCapRays;
+    a.capInterior = h->tileCapInterior;
+    a.levels = h->levels;
+    a.tileRays = (int)R;
+    a.stackEntries = h->stackEntries;
+    a.tileCursor = &h->dFrame()->tileCursor[pass];
+    a.ctr = h->dFrame();
+    a.lv = h->dLevel(pass, 0);
+    a.gen = gen;
+    a.userQ = userQ;
+    a.nUser = nUser;
+    a.stagedMesh = staged ? h->scene.meshes + h->stagedMeshIndex : nullptr;
+    a.stagedNodesSrc = h->stagedNodesSrc;
+    a.stagedTrisSrc = h->stagedTrisSrc;
+    a.stagedNodes = h->stagedNodes;
+    a.stagedTris = h->stagedTris;
+    KernelSpan ks(h, st, pass == 0 ? RTB_K_TILE : RTB_K_TILE_SSAA);
+    if (staged) {
+        if (genKind == rtk::GEN_PRIMARY) launchTileStaged<rtk::GEN_PRIMARY>(deep, h->stagedAttrSet[genKind], h->smemOptin, grid, smem, st, h->scene, a);
+        else if (genKind == rtk::GEN_SSAA) launchTileStaged<rtk::GEN_SSAA>(deep, h->stagedAttrSet[genKind], h->smemOptin, grid, smem, st, h->scene, a);
+        else launchTileStaged<rtk::GEN_QUEUE>(deep, h->stagedAttrSet[genKind], h->smemOptin, grid, smem, st, h->scene, a);
+    }
+    else if (genKind == rtk::GEN_PRIMARY) launchTileGen<rtk::GEN_PRIMARY>(deep, stats, grid, smem, st, h->scene, a);
+    else if (genKind == rtk::GEN_SSAA) launchTileGen<rtk::GEN_SSAA>(deep, stats, grid, smem, st, h->scene, a);
+    else launchTileGen<rtk::GEN_QUEUE>(deep, stats, grid, smem, st, h->scene, a);
+    ks.done();
 }
 
 // Enqueues castRay for the rays sitting in queue 0 of `pass`, level by level, then folds the interior
@@ -417,6 +543,11 @@ int finishFrame(RtbHandle* h, cudaStream_t st, int passes)
 void growAfterOverflow(RtbHandle* h, int bits, int passes)
 {
     if (bits & rtk::OVF_FLAGGED) h->capFlagged = std::max(2 * h->capFlagged, (long long)h->hFrame()->ssaaPixels);
+    if (h->tilePipeline) {   // per-tile capacities: the counters do not say how much one tile wanted, so double
+        if (bits & rtk::OVF_RAYS) h->tileCapRays *= 2;
+        if (bits & rtk::OVF_INTERIORS) h->tileCapInterior *= 2;
+        return;
+    }
     if (bits & rtk::OVF_RAYS) {
         long long want = 2 * h->capDeep;
         for (int p = 0; p < passes; ++p)
@@ -483,7 +614,8 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
 
     for (int attempt = 0;; ++attempt) {
         const long long level0 = std::max(n0, 4 * std::max(flaggedCap, h->capFlagged));
-        ensureCapacity(h, st, framePixels, level0, 2 * level0, 2 * level0, flaggedCap);
+        const bool tile = h->tilePipeline;
+        ensureCapacity(h, st, framePixels, level0, 2 * level0, 2 * level0, flaggedCap, !tile);
         const int sampleBase = (int)framePixels;
 
         CK(cudaEventRecord(h->ev[0], st));
@@ -501,6 +633,8 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                 rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)genRows.size(), h->rays[0].view(), h->dLevel(0, 0));
                 ks.done();
                 enqueueLevels(h, st, 0, framePixels);
+            } else if (tile) {
+                enqueueTile(h, st, 0, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)genRows.size(), -1, genX0, genCols, h->slots.as<float>(), h->sceneDev }, n0);
             } else {
                 enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)genRows.size(), 0, genX0, genCols, h->slots.as<float>(), h->sceneDev });
             }
@@ -550,13 +684,20 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                     h->rays[0].view(), h->dFrame(), h->dLevel(1, 0));
                 ks.done();
                 enqueueLevels(h, st, 1, framePixels);
+            } else if (tile) {
+                // the tile kernel also takes the mean of each pixel's 4 samples: no separate resolve
+                const long long hint = 4 * std::max(1024LL, h->flaggedSeen > 0 ? h->flaggedSeen : h->capFlagged / 4);
+                enqueueTile(h, st, 1, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, -1, 0, 0, h->slots.as<float>(), h->sceneDev },
+                    std::min(hint, 4 * h->capFlagged));
             } else {
                 enqueueLevels(h, st, 1, framePixels, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, sampleBase, 0, 0, h->slots.as<float>(), h->sceneDev });
             }
-            KernelSpan ks(h, st, RTB_K_OUTPUT);
-            rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
-                h->slots.as<float>(), h->dFrame());
-            ks.done();
+            if (!tile) {
+                KernelSpan ks(h, st, RTB_K_OUTPUT);
+                rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
+                    h->slots.as<float>(), h->dFrame());
+                ks.done();
+            }
         } else {
             CK(cudaEventRecord(h->ev[2], st));
         }
@@ -578,6 +719,7 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     resolveSpans(h);
     h->flaggedSeen = (long long)h->stats.ssaaPixels;
     h->stats.primaryRays = (uint64_t)nPixels + 4 * h->stats.ssaaPixels;
+    h->stats.backgroundPixels = (uint64_t)(nPixels - (culled ? (long long)genRows.size() * genCols : nPixels));
     h->stats.rays = h->stats.primaryRays + h->stats.secondaryRays + h->stats.shadowRays;
     h->stats.msPass1 = elapsed(h->ev[0], h->ev[1]);
     h->stats.msSobel = elapsed(h->ev[1], h->ev[2]);
@@ -592,13 +734,18 @@ void enqueueUserRays(RtbHandle* h, cudaStream_t st, const float* rays, int nRays
 {
     beginCall(h);
     for (int attempt = 0;; ++attempt) {
-        ensureCapacity(h, st, nRays, nRays, 2LL * nRays, 2LL * nRays, 0);
+        {
+            const bool tileCast = shade && h->tilePipeline;
+            ensureCapacity(h, st, nRays, nRays, tileCast ? 0 : 2LL * nRays, tileCast ? 0 : 2LL * nRays, 0);
+        }
         h->userRays.reserve((size_t)nRays * 6 * sizeof(float), st, false);
         CK(cudaMemcpyAsync(h->userRays.p, rays, (size_t)nRays * 6 * sizeof(float), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
         rtk::k_rays_from_user<<<gridFor(h, nRays), rtk::kBlock, 0, st>>>(h->userRays.as<float>(), nRays, 0, h->rays[0].view(), h->dLevel(0, 0));
         launchCheck();
-        if (shade) {
+        if (shade && h->tilePipeline) {
+            enqueueTile(h, st, 0, rtk::GEN_QUEUE, rtk::GenArgs{ nullptr, 0, -1, 0, 0, h->slots.as<float>(), h->sceneDev }, nRays, h->rays[0].view(), nRays);
+        } else if (shade) {
             enqueueLevels(h, st, 0, nRays);
         } else {
             const rtk::HitQueue hits{ h->hitTuv.as<float4>(), h->hitObj.as<int>() };
@@ -653,7 +800,7 @@ void destroyHandle(RtbHandle* h)
     for (void* p : h->allocations) cudaFree(p);
     h->rays[0].release(); h->rays[1].release();
     for (DevBuf* b : { &h->hitTuv, &h->hitObj, &h->surfP, &h->surfN, &h->surfC, &h->vis, &h->interiors, &h->slots, &h->flagged,
-             &h->rowsA, &h->rowsB, &h->userRays, &h->outStage })
+             &h->rowsA, &h->rowsB, &h->userRays, &h->outStage, &h->tileSlab })
         b->release();
     h->ctrBuf.release();
     if (h->hCtr) cudaFreeHost(h->hCtr);
@@ -686,6 +833,8 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         h->device = device;
         h->createFlags = createFlags;
         h->kernelTiming = createFlags & RTB_CREATE_KERNEL_TIMING;
+        // the literal reference walk (parity of work counters) only exists in the frame-wide form
+        h->tilePipeline = !(createFlags & (RTB_CREATE_WAVEFRONT | RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK));
         cudaDeviceProp prop{};
         CK(cudaGetDeviceProperties(&prop, device));
         h->smCount = prop.multiProcessorCount;
@@ -717,7 +866,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             if (createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK)) h->stackEntries = std::max(h->stackEntries, pm.maxDepth + 1);
             // a mesh whose .obj yields no usable face still has a one-node tree (objects.cpp:389): nothing to search, the
             // kernels skip it (bvhTris stays null)
-            if (m.nNodes > 0 && m.nTris > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d) + 1);
+            if (m.nNodes > 0 && m.nTris > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d, i) + 1);
             meshes.push_back(d);
         }
         for (int i = 0; i < s->nObjects; ++i) rtpack::objectBounds(s->objects[i], h->geomBounds, h->unbounded);
@@ -727,6 +876,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         for (int i = 0; i < s->nObjects; ++i)
             spawns |= s->objects[i].material == RTB_MAT_REFLECTIVE || s->objects[i].material == RTB_MAT_TRANSPARENT;
         h->levels = spawns ? std::max(0, s->maxRayDepth) + 1 : 1;
+        if (h->levels > rtk::kMaxTileLevels) h->tilePipeline = false;   // the per-tile level table is fixed-size; deeper trees run frame-wide
         h->ctrBytes = sizeof(rtk::FrameCtr) + 2 * (size_t)(h->levels + 1) * sizeof(rtk::LevelCtr);
         h->ctrBuf.reserve(h->ctrBytes, h->ownStream, false);
         CK(cudaMallocHost(&h->hCtr, h->ctrBytes));
@@ -740,6 +890,18 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         h->scene.objects = upload(h, objects.data(), objects.size());
         h->scene.lights = upload(h, lights.data(), lights.size());
         h->scene.meshes = upload(h, meshes.data(), meshes.size());
+        // staged tile kernel: how much of the largest search BVH fits into shared memory next to four groups' stacks
+        h->smemOptin = prop.sharedMemPerBlockOptin;
+        if (h->stagedMeshIndex >= 0) {
+            const rt::Mesh& sm = meshes[h->stagedMeshIndex];
+            h->stagedNodesSrc = sm.bvhNodes;
+            h->stagedTrisSrc = sm.bvhTris;
+            const long long avail = (long long)h->smemOptin - 1024 - (long long)rtk::tileSmemStagedOffset(kStagedGroups, h->stackEntries);
+            h->stagedNodes = (int)std::max(0LL, std::min<long long>(h->stagedNodesAll, avail / 64));
+            const long long left = avail - (long long)h->stagedNodes * 64;
+            h->stagedTris = (h->stagedNodes == h->stagedNodesAll && left >= (long long)h->stagedTrisAll * 48) ? h->stagedTrisAll : 0;
+        }
+        if (const char* e = getenv("RTB_TILE_STAGED")) h->tileStaged = atoi(e) != 0;
         h->scene.areaPoints = upload(h, s->areaPoints, (size_t)s->nAreaPoints * 3);
         if (s->flags & RTB_FLAG_USE_SKYBOX)
             for (int k = 0; k < 6; ++k) h->scene.sky[k] = uploadImage(h, s->skybox[k]);

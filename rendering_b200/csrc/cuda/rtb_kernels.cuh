@@ -46,6 +46,7 @@ struct FrameCtr {
     int overflow;        // OVF_* bits: a queue would have overflowed its capacity -> the host grows it and re-runs
     unsigned int shadowSkipped;   // shadow rays not traced because their result cannot affect the pixel
     int acMax;           // showAC debug view: largest per-pixel box count
+    unsigned long long tileCursor[2];   // tile pipeline: next tile of pass 1 / of the SSAA pass
     unsigned long long boxTests, triTests;             // closest-hit rays (counting build)
     unsigned long long boxTestsShadow, triTestsShadow; // shadow rays (counting build)
     // fast path's own work (RTB_CREATE_WALK_STATS): search-BVH nodes fetched, triangles tested, eligibility evaluations
@@ -97,6 +98,29 @@ __device__ __forceinline__ void storeSlot(float* slots, int s, V3 c)
 __device__ __forceinline__ V3 loadSlot(const float* slots, int s)
 {
     const float* p = slots + (size_t)s * 3;
+    return mk(p[0], p[1], p[2]);
+}
+
+// Where colours go.  `dest` >= 0 names a slot of the frame-wide array `g` (slots [0, w*h) are the framebuffer);
+// `dest` <= -2 names slot (-2 - dest) of the tile-local array `l` (SSAA samples and children of Reflective /
+// Transparent hits of the tile pipeline, rtb_tile.cuh).  -1 marks a padding queue entry.
+struct Slots {
+    float* g;
+    float* l;
+};
+__device__ __forceinline__ int localDest(int slot) { return -2 - slot; }
+__device__ __forceinline__ float* slotAddr(const Slots& s, int dest)
+{
+    return dest >= 0 ? s.g + (size_t)dest * 3 : s.l + (size_t)(-2 - dest) * 3;
+}
+__device__ __forceinline__ void storeSlot(const Slots& s, int dest, V3 c)
+{
+    float* p = slotAddr(s, dest);
+    p[0] = c.x; p[1] = c.y; p[2] = c.z;
+}
+__device__ __forceinline__ V3 loadSlot(const Slots& s, int dest)
+{
+    const float* p = slotAddr(s, dest);
     return mk(p[0], p[1], p[2]);
 }
 
@@ -250,18 +274,19 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int cap,
 // ------------------------------------------------------------------------------------------------
 // surface stage: castRay between trace() and the light loops (scene.cpp:762-775, 945)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
-    float* __restrict__ slots, LevelCtr* lv, int handleMisses)
+// Threads `first`, `first + step`, ... of a group of `step` threads (a multiple of 32) share the work; `nSurf` is the
+// group's compaction counter (global memory for the frame-wide pipeline, shared memory for a tile).
+__device__ __forceinline__ void surfaceStage(const Scene& sc, RayQueue q, HitQueue hits, SurfQueue surf, const Slots& slots, int n, int first, int step,
+    int* nSurf, int handleMisses)
 {
-    const int n = min(lv->nRays, cap);
     const int nPadded = (n + 31) & ~31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nPadded; i += gridDim.x * blockDim.x) {
+    for (int i = first; i < nPadded; i += step) {
         bool wantSurface = false;
         Surface s;
         int obj = -1;
-        // rays generated inside k_walk resolve their own misses (handleMisses == 0): only obj is valid for those
+        // rays generated inside the walk resolve their own misses (handleMisses == 0): only obj is valid for those
         if (i < n) obj = hits.obj[i];
-        if (i < n && (obj >= 0 || (handleMisses && q.dest[i] >= 0))) {
+        if (i < n && (obj >= 0 || (handleMisses && q.dest[i] != -1))) {
             const float4 d4 = q.d[i];
             const V3 d = mk(d4.x, d4.y, d4.z);
             if (obj < 0) {
@@ -273,13 +298,20 @@ __global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int ca
                 else wantSurface = true;
             }
         }
-        const int si = warpAlloc(&lv->nSurf, wantSurface, 1);
+        const int si = warpAlloc(nSurf, wantSurface, 1);
         if (wantSurface) {
             surf.pS[si] = make_float4(s.P.x, s.P.y, s.P.z, s.specCoef);
             surf.nO[si] = make_float4(s.N.x, s.N.y, s.N.z, __int_as_float(obj));
             surf.cR[si] = make_float4(s.color.x, s.color.y, s.color.z, __int_as_float(i));
         }
     }
+}
+
+__global__ void __launch_bounds__(kBlock) k_surface(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
+    float* __restrict__ slots, LevelCtr* lv, int handleMisses)
+{
+    surfaceStage(sc, q, hits, surf, Slots{ slots, nullptr }, min(lv->nRays, cap), blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x,
+        &lv->nSurf, handleMisses);
 }
 
 // light sample k of a surface: direction FROM the light (normalised for point / area) and distance
@@ -406,41 +438,63 @@ enum { GEN_QUEUE = 0, GEN_PRIMARY = 1, GEN_SSAA = 2 };
 struct GenArgs {
     const int* list;     // GEN_PRIMARY: image rows to render; GEN_SSAA: flagged pixels
     int count;           // GEN_PRIMARY: number of rows; GEN_SSAA: capacity of the flagged list
-    int slotBase;        // GEN_SSAA: first sample slot
+    int slotBase;        // GEN_SSAA: first sample slot of the frame-wide slot array; -1 = samples go to tile-local slots
     int x0, cols;        // GEN_PRIMARY: pixel columns [x0, x0 + cols) to generate rays for (the screen-space bounds of the
                          // geometry; pixels outside were pre-filled with the background colour by k_fill_background)
-    float* slots;        // colour slots (misses of generated rays are resolved here)
+    float* slots;        // frame-wide colour slots (misses of generated rays are resolved here)
     const Scene* scene;  // device-resident copy of the scene header for the out-of-line helpers below
 };
 
 // Kept out of line so their FP64 normalisation / cube-map code does not raise the register count of the
 // traversal loop (they run once per ray, the loop runs ~100 times).
 __device__ __noinline__ V3 genCameraRay(const Scene* sc, float px, float py) { return cameraDir(*sc, px, py); }
-__device__ __noinline__ void storeMissColour(const Scene* sc, float* slots, int dest, V3 d) { storeSlot(slots, dest, skybox(*sc, d)); }
+__device__ __noinline__ void storeMissColour(const Scene* sc, float* p, V3 d)
+{
+    const V3 c = skybox(*sc, d);
+    p[0] = c.x; p[1] = c.y; p[2] = c.z;
+}
 
 #ifndef RTB_WALK_MIN_BLOCKS
 #define RTB_WALK_MIN_BLOCKS 9   // 56 registers, 9 CTAs per SM: measured 1-2 % faster than 64 / 78 registers at 8 / 6 CTAs
 #endif
-template <bool ANY, int GEN, bool STATS = false>
-__global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
-    unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv, GenArgs gen)
+
+// Part of one mesh's search BVH resident in shared memory (rtb_tile.cuh stages it with TMA bulk copies): nodes
+// [0, nNodes) — the tree's top levels, or all of it — and, when the whole mesh fits, every leaf triangle.
+struct StagedBvh {
+    const Mesh* mesh;        // the mesh the copy belongs to (nullptr = nothing staged)
+    unsigned nodesAddr;      // shared-memory byte addresses
+    unsigned trisAddr;
+    int nNodes;
+    int nTris;               // 0 = triangles stay in global memory
+};
+__device__ __forceinline__ float4 ldsF4(unsigned addr)
 {
-    extern __shared__ int stackMem[];
-    int* stack = stackMem + threadIdx.x;
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// per-thread tallies of a walk, flushed by the caller (once per kernel)
+struct WalkAcc {
+    unsigned nSkipped = 0;                                 // shadow rays elided
+    unsigned long long nNodes = 0, nTris = 0, nElig = 0;   // STATS only
+};
+
+// The traversal loop.  All 32 lanes of a warp must call it together; warps are otherwise independent and pull rays
+// [0, total) from `cursor` (global memory for a frame-wide launch, shared memory for one tile's stage).  Indices are
+// relative to the queues handed in; generated rays map index `my` to pixel / sample number genOffset + my.
+// STRIDE = distance in ints between a thread's consecutive stack entries (the thread count of the stack's owner).
+template <bool ANY, int GEN, bool STATS, int STRIDE, typename CursorT, bool STAGED = false>
+__device__ __forceinline__ void walkRays(const Scene& sc, RayQueue q, HitQueue hits, SurfQueue surf, unsigned char* vis, int nSurfRaw,
+    const GenArgs& gen, long long genOffset, const Slots& slots, CursorT* cursor, long long total, int* stack, WalkAcc& acc,
+    const StagedBvh& sb = StagedBvh{})
+{
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lanesBelow = (1u << lane) - 1;
     const bool cull = sc.flags & FLAG_CULL;
     const int S = sc.shadowRaysPerHit;
-    unsigned long long* cursor = &lv->cursor[ANY ? 1 : 0];
-    const int nSurfRaw = ANY ? lv->nSurf : 0;
     const int nSurf = nSurfRaw > 0 ? nSurfRaw : 1;
-    long long total;
-    if (ANY) total = (long long)nSurfRaw * S;
-    else if (GEN == GEN_PRIMARY) total = raygenPaddedCount(gen.cols + 1, gen.count);
-    else if (GEN == GEN_SSAA) total = 4LL * min(ctr->ssaaPixels, gen.count);
-    else total = min(lv->nRays, cap);
-    if (!ANY && GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
     const int tilesX = (gen.cols + 7) / 8;
 
     bool have = false, exhausted = false;
@@ -455,11 +509,9 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
     bool found = false;
     int slotBest = 0x7fffffff, triM = -1;
     float tM = FLT_MAX, uM = 0.f, vM = 0.f;
-    unsigned nSkipped = 0;
-    unsigned long long nNodes = 0, nTris = 0, nElig = 0;   // STATS only
 
     for (;;) {
-        // ---- refill idle lanes from the global cursor ----
+        // ---- refill idle lanes from the cursor ----
         // One atomicAdd per refill hands every idle lane the next consecutive ray.  kRefillBelow = 1: a warp takes
         // 32 consecutive rays and finishes them all before fetching again.  Measured on B200 (cfg4 / dragon frame ms):
         // refilling when fewer than 22 / 16 / 10 / 6 / 1 lanes are live gives 0.677 / 0.661 / 0.655 / 0.565 / 0.565 and
@@ -470,7 +522,7 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
         if (idle && !exhausted) {
             const int nIdle = __popc(idle), leader = __ffs(idle) - 1;
             unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(cursor, (unsigned long long)nIdle);
+            if (lane == leader) base = (unsigned long long)atomicAdd(cursor, (CursorT)nIdle);
             base = __shfl_sync(FULL, base, leader);
             if ((long long)base + nIdle >= total) exhausted = true;
             const long long my = (long long)base + __popc(idle & lanesBelow);
@@ -480,10 +532,11 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                     bool live = true;
                     V3 o, d;
                     if (GEN == GEN_PRIMARY) {
-                        const long long tile = my >> 5;
-                        const int xr = (int)(tile % tilesX) * 8 + ((int)my & 7);
+                        const long long gmy = genOffset + my;
+                        const long long tile = gmy >> 5;
+                        const int xr = (int)(tile % tilesX) * 8 + ((int)gmy & 7);
                         const int x = gen.x0 + xr;
-                        const int rr = (int)(tile / tilesX) * 4 + (((int)my >> 3) & 3);
+                        const int rr = (int)(tile / tilesX) * 4 + (((int)gmy >> 3) & 3);
                         live = xr < gen.cols && rr < gen.count;
                         if (live) {
                             const int y = __ldg(gen.list + rr);
@@ -492,15 +545,16 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                             dest = y * sc.width + x;
                         }
                     } else if (GEN == GEN_SSAA) {
-                        const int pix = __ldg(gen.list + (my >> 2)), k = (int)my & 3;
+                        const long long gmy = genOffset + my;
+                        const int pix = gen.list[gmy >> 2], k = (int)gmy & 3;
                         const int y = pix / sc.width, x = pix - y * sc.width;
                         // sample order (.25,.25) (.25,.75) (.75,.25) (.75,.75)  (scene.cpp:527-534)
                         const float ox = (k & 2) ? 0.75f : 0.25f, oy = (k & 1) ? 0.75f : 0.25f;
                         o = sc.camPos;
                         d = genCameraRay(gen.scene, (float)x + ox, (float)y + oy);
-                        dest = gen.slotBase + (int)my;
+                        dest = gen.slotBase < 0 ? localDest((int)my) : gen.slotBase + (int)gmy;
                     } else {
-                        live = q.dest[my] >= 0;      // padding entry
+                        live = q.dest[my] != -1;     // padding entry
                         if (live) {
                             const float4 o4 = q.o[my], d4 = q.d[my];
                             o = mk(o4.x, o4.y, o4.z); d = mk(d4.x, d4.y, d4.z);
@@ -531,7 +585,7 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                         needed = base2 > 0.f || (!areaSample && !(ob.nSpecular > 0.f));
                     }
                     out = (long long)si * S + k;
-                    if (!needed) { vis[out] = 0; nSkipped++; }
+                    if (!needed) { vis[out] = 0; acc.nSkipped++; }
                     else {
                         r = makeRay(P + N * sc.bias, -L);
                         tNear = dist; obj = 0; cur = kDone; have = true;
@@ -555,7 +609,7 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                         } else {
                             hits.obj[out] = objN;
                             if (objN < 0) {
-                                storeMissColour(gen.scene, gen.slots, dest, r.d);          // castRay's miss branch (scene.cpp:945)
+                                storeMissColour(gen.scene, slotAddr(slots, dest), r.d);    // castRay's miss branch (scene.cpp:945)
                             } else {
                                 hits.tuv[out] = make_float4(tNear, uN, vN, __int_as_float(triN));
                                 q.o[out] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
@@ -598,9 +652,15 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                 const bool runInner = innerM != 0 && __popc(leafM) < kLeafBatch;
                 if (runInner && atInner) {
                     for (int step = 0; step < kInnerSteps && cur >= 0; ++step) {
-                        const float4* nd = me->bvhNodes + (size_t)cur * 4;
-                        const float4 a = __ldg(nd), b = __ldg(nd + 1), c = __ldg(nd + 2), d = __ldg(nd + 3);
-                        if (STATS) nNodes++;
+                        float4 a, b, c, d;
+                        if (STAGED && me == sb.mesh && cur < sb.nNodes) {
+                            const unsigned na = sb.nodesAddr + (unsigned)cur * 64u;
+                            a = ldsF4(na); b = ldsF4(na + 16); c = ldsF4(na + 32); d = ldsF4(na + 48);
+                        } else {
+                            const float4* nd = me->bvhNodes + (size_t)cur * 4;
+                            a = __ldg(nd); b = __ldg(nd + 1); c = __ldg(nd + 2); d = __ldg(nd + 3);
+                        }
+                        if (STATS) acc.nNodes++;
                         const float tFar = ANY ? tNear : tM;
                         bool h0, h1;
                         const float e0 = slabEntry(r, a.x, a.y, a.z, a.w, b.x, b.y, tFar, h0);
@@ -608,12 +668,12 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                         const int c0 = __float_as_int(d.x), c1 = __float_as_int(d.y);
                         if (h0 && h1) {
                             const bool swap = e1 < e0;
-                            stack[sp * kBlock] = swap ? c0 : c1;
+                            stack[sp * STRIDE] = swap ? c0 : c1;
                             sp++;
                             cur = swap ? c1 : c0;
                         } else if (h0) cur = c0;
                         else if (h1) cur = c1;
-                        else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
+                        else if (sp > 0) { sp--; cur = stack[sp * STRIDE]; }
                         else { cur = kDone; break; }
                     }
                     if (cur == kDone) {   // mesh finished
@@ -624,24 +684,28 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
                     const int code = ~cur;
                     const int first = code >> 3, count = (code & 7) + 1;
                     const float4* tp = me->bvhTris + (size_t)first * 3;
+                    const bool trisStaged = STAGED && me == sb.mesh && sb.nTris > 0;
+                    unsigned ta = sb.trisAddr + (unsigned)first * 48u;
                     bool blocked = false;
-                    for (int k = 0; k < count; ++k, tp += 3) {
-                        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                    for (int k = 0; k < count; ++k, tp += 3, ta += 48u) {
+                        float4 p0, p1, p2;
+                        if (trisStaged) { p0 = ldsF4(ta); p1 = ldsF4(ta + 16); p2 = ldsF4(ta + 32); }
+                        else { p0 = __ldg(tp); p1 = __ldg(tp + 1); p2 = __ldg(tp + 2); }
                         float t, u, v;
-                        if (STATS) nTris++;
+                        if (STATS) acc.nTris++;
                         if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
                         const int tri = __float_as_int(p0.w);
                         if (ANY) {
-                            if (STATS && t < tNear) nElig++;
+                            if (STATS && t < tNear) acc.nElig++;
                             if (t < tNear && eligibleSlot(sc, *me, r, tri) >= 0) { blocked = true; break; }
                         } else if (t < tM || (found && t == tM)) {
-                            if (STATS) nElig++;
+                            if (STATS) acc.nElig++;
                             const int slot = eligibleSlot(sc, *me, r, tri);
                             if (slot >= 0 && (t < tM || slot < slotBest)) { tM = t; uM = u; vM = v; triM = tri; slotBest = slot; found = true; }
                         }
                     }
                     if (ANY && blocked) { vis[out] = 0; have = false; cur = kDone; }
-                    else if (sp > 0) { sp--; cur = stack[sp * kBlock]; }
+                    else if (sp > 0) { sp--; cur = stack[sp * STRIDE]; }
                     else {
                         cur = kDone;
                         if (!ANY && found) { tNear = tM; uN = uM; vN = vM; objN = obj; triN = triM; }
@@ -653,11 +717,41 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
             if (act == 0 || (!exhausted && __popc(act) < kRefillBelow)) break;
         }
     }
-    if (ANY && nSkipped) atomicAdd(&ctr->shadowSkipped, nSkipped);
+}
+
+__device__ __forceinline__ void flushWalkAcc(FrameCtr* ctr, const WalkAcc& acc, bool stats)
+{
+    // one atomic per warp, not per thread
+    unsigned sk = acc.nSkipped;
+    for (int o = 16; o > 0; o >>= 1) sk += __shfl_xor_sync(0xffffffffu, sk, o);
+    if ((threadIdx.x & 31) == 0 && sk) atomicAdd(&ctr->shadowSkipped, sk);
+    (void)stats;
+}
+
+// The frame-wide form: one launch walks one level's whole queue (the grid is sized to the machine, every warp pulls
+// batches from the level's global cursor).  The default pipeline runs the same loop per tile inside k_tile (rtb_tile.cuh).
+template <bool ANY, int GEN, bool STATS = false>
+__global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, RayQueue q, int cap, HitQueue hits, SurfQueue surf,
+    unsigned char* __restrict__ vis, FrameCtr* ctr, LevelCtr* lv, GenArgs gen)
+{
+    extern __shared__ int stackMem[];
+    int* stack = stackMem + threadIdx.x;
+    const int S = sc.shadowRaysPerHit;
+    unsigned long long* cursor = &lv->cursor[ANY ? 1 : 0];
+    const int nSurfRaw = ANY ? lv->nSurf : 0;
+    long long total;
+    if (ANY) total = (long long)nSurfRaw * S;
+    else if (GEN == GEN_PRIMARY) total = raygenPaddedCount(gen.cols + 1, gen.count);
+    else if (GEN == GEN_SSAA) total = 4LL * min(ctr->ssaaPixels, gen.count);
+    else total = min(lv->nRays, cap);
+    if (!ANY && GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
+    WalkAcc acc;
+    walkRays<ANY, GEN, STATS, kBlock>(sc, q, hits, surf, vis, nSurfRaw, gen, 0LL, Slots{ gen.slots, nullptr }, cursor, total, stack, acc);
+    if (ANY) flushWalkAcc(ctr, acc, STATS);
     if (STATS) {
-        atomicAdd(&ctr->walkNodes[ANY ? 1 : 0], nNodes);
-        atomicAdd(&ctr->walkTris[ANY ? 1 : 0], nTris);
-        atomicAdd(&ctr->walkEligibility[ANY ? 1 : 0], nElig);
+        atomicAdd(&ctr->walkNodes[ANY ? 1 : 0], acc.nNodes);
+        atomicAdd(&ctr->walkTris[ANY ? 1 : 0], acc.nTris);
+        atomicAdd(&ctr->walkEligibility[ANY ? 1 : 0], acc.nElig);
     }
 }
 
@@ -667,15 +761,25 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
 #ifndef RTB_SHADE_MIN_BLOCKS
 #define RTB_SHADE_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(kBlock, RTB_SHADE_MIN_BLOCKS) k_shade(Scene sc, RayQueue q, SurfQueue surf, const unsigned char* __restrict__ vis,
-    int depth, RayQueue next, int nextCap, Interior* __restrict__ interiors, int interiorCap,
-    float* __restrict__ slots, int slotBase, int slotCap, FrameCtr* ctr, LevelCtr* lv)
+
+// Where a shade stage puts what it spawns.  Frame-wide pipeline: global counters, child colours in the frame-wide slot
+// array from slotBase on (slotCount hands them out).  Tile pipeline: the group's shared-memory counters, child colours
+// in the tile-local slot array (record i owns local slots slotBase + 2 i, slotCount == nullptr).
+struct ShadeOut {
+    RayQueue next; int nextCap; int* nextCount;
+    Interior* interiors; int interiorCap; int* interiorCount;
+    int* interiorEnd;        // frame-wide only: atomicMax of (record index + 1) per level
+    int* slotCount; int slotBase, slotCap;
+    bool localSlots;
+    int* overflow;
+};
+
+__device__ __forceinline__ void shadeStage(const Scene& sc, RayQueue q, SurfQueue surf, const unsigned char* vis, int depth, int n, int first, int step,
+    const Slots& slots, const ShadeOut& o)
 {
     const int S = sc.shadowRaysPerHit;
-    const int n = lv->nSurf;
-    LevelCtr* lvNext = lv + 1;
     const int nPadded = (n + 31) & ~31;
-    for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < nPadded; si += gridDim.x * blockDim.x) {
+    for (int si = first; si < nPadded; si += step) {
         int nChildren = 0;
         bool wantInterior = false;
         Interior rec;
@@ -764,42 +868,73 @@ __global__ void __launch_bounds__(kBlock, RTB_SHADE_MIN_BLOCKS) k_shade(Scene sc
             }
         }
         // bump-allocate: interior record, two colour slots, nChildren queue entries
-        const int ii = warpAlloc(&ctr->interiors, wantInterior, 1);
-        const int cs = slotBase + warpAlloc(&ctr->slots, wantInterior, 2);
-        const int q1 = warpAlloc(&lvNext->nRays, nChildren >= 1, 1);
-        const int q2 = warpAlloc(&lvNext->nRays, nChildren >= 2, 1);
+        const int ii = warpAlloc(o.interiorCount, wantInterior, 1);
+        const int cs = o.slotBase + (o.slotCount ? warpAlloc(o.slotCount, wantInterior, 2) : 2 * ii);
+        const int q1 = warpAlloc(o.nextCount, nChildren >= 1, 1);
+        const int q2 = warpAlloc(o.nextCount, nChildren >= 2, 1);
         if (wantInterior) {
-            const bool fits1 = q1 < nextCap, fits2 = nChildren < 2 || q2 < nextCap;
-            if (ii >= interiorCap || cs + 2 > slotCap) {
-                atomicOr(&ctr->overflow, OVF_INTERIORS);
+            const bool fits1 = q1 < o.nextCap, fits2 = nChildren < 2 || q2 < o.nextCap;
+            if (ii >= o.interiorCap || cs + 2 > o.slotCap) {
+                atomicOr(o.overflow, OVF_INTERIORS);
                 // queue entries already claimed must not stay uninitialised: mark them as padding
-                if (fits1) next.dest[q1] = -1;
-                if (nChildren == 2 && fits2) next.dest[q2] = -1;
+                if (fits1) o.next.dest[q1] = -1;
+                if (nChildren == 2 && fits2) o.next.dest[q2] = -1;
             } else {
-                if (!fits1 || !fits2) atomicOr(&ctr->overflow, OVF_RAYS);   // the host re-runs the frame with larger queues
+                if (!fits1 || !fits2) atomicOr(o.overflow, OVF_RAYS);   // the host re-runs the frame with larger queues
                 rec.child = cs;
-                interiors[ii] = rec;
-                atomicMax(&lv->interiorEnd, ii + 1);
-                // kind 3 keeps its single (reflection) child in slot child+1 so k_combine reads one layout
+                o.interiors[ii] = rec;
+                if (o.interiorEnd) atomicMax(o.interiorEnd, ii + 1);
+                // kind 3 keeps its single (reflection) child in slot child+1 so the combine stage reads one layout
                 const int firstSlot = (rec.kind == 3) ? cs + 1 : cs;
+                const int d1 = o.localSlots ? localDest(firstSlot) : firstSlot, d2 = o.localSlots ? localDest(cs + 1) : cs + 1;
                 if (fits1) {
-                    next.o[q1] = make_float4(childO[0].x, childO[0].y, childO[0].z, 0.0f);
-                    next.d[q1] = make_float4(childD[0].x, childD[0].y, childD[0].z, 0.0f);
-                    next.dest[q1] = firstSlot;
-                } else storeSlot(slots, firstSlot, mk(0.0f, 0.0f, 0.0f));
+                    o.next.o[q1] = make_float4(childO[0].x, childO[0].y, childO[0].z, 0.0f);
+                    o.next.d[q1] = make_float4(childD[0].x, childD[0].y, childD[0].z, 0.0f);
+                    o.next.dest[q1] = d1;
+                } else storeSlot(slots, d1, mk(0.0f, 0.0f, 0.0f));
                 if (nChildren == 2) {
                     if (fits2) {
-                        next.o[q2] = make_float4(childO[1].x, childO[1].y, childO[1].z, 0.0f);
-                        next.d[q2] = make_float4(childD[1].x, childD[1].y, childD[1].z, 0.0f);
-                        next.dest[q2] = cs + 1;
-                    } else storeSlot(slots, cs + 1, mk(0.0f, 0.0f, 0.0f));
+                        o.next.o[q2] = make_float4(childO[1].x, childO[1].y, childO[1].z, 0.0f);
+                        o.next.d[q2] = make_float4(childD[1].x, childD[1].y, childD[1].z, 0.0f);
+                        o.next.dest[q2] = d2;
+                    } else storeSlot(slots, d2, mk(0.0f, 0.0f, 0.0f));
                 }
             }
         }
     }
 }
 
-// Fold children into parents for interior records [first, last): castRay's return path.
+__global__ void __launch_bounds__(kBlock, RTB_SHADE_MIN_BLOCKS) k_shade(Scene sc, RayQueue q, SurfQueue surf, const unsigned char* __restrict__ vis,
+    int depth, RayQueue next, int nextCap, Interior* __restrict__ interiors, int interiorCap,
+    float* __restrict__ slots, int slotBase, int slotCap, FrameCtr* ctr, LevelCtr* lv)
+{
+    const ShadeOut o{ next, nextCap, &(lv + 1)->nRays, interiors, interiorCap, &ctr->interiors, &lv->interiorEnd, &ctr->slots, slotBase, slotCap,
+        false, &ctr->overflow };
+    shadeStage(sc, q, surf, vis, depth, lv->nSurf, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, Slots{ slots, nullptr }, o);
+}
+
+// Fold children into parents for interior records [first, last): castRay's return path.  rec.child is a slot INDEX of
+// the frame-wide array, or of the tile-local array when localChildren.
+__device__ __forceinline__ void combineStage(const Interior* interiors, int first, int last, int tid, int step, const Slots& slots, bool localChildren)
+{
+    for (int i = first + tid; i < last; i += step) {
+        const Interior rec = interiors[i];
+        const V3 spec = mk(rec.sx, rec.sy, rec.sz);
+        const int c0 = localChildren ? localDest(rec.child) : rec.child, c1 = localChildren ? localDest(rec.child + 1) : rec.child + 1;
+        V3 c;
+        if (rec.kind == 1) {
+            c = loadSlot(slots, c0) * 0.8f;                        // hitColor = 0.8f * castRay(...)   (:858)
+            c = c + spec;                                          // hitColor += specularComponent    (:890)
+        } else {
+            c = mk(0.0f, 0.0f, 0.0f);                              // hitColor = { 0 }                 (:896)
+            if (rec.kind == 2) c = c + loadSlot(slots, c0) * (1 - rec.kr);   // :902
+            c = c + loadSlot(slots, c1) * rec.kr;                  // :908
+            c = c + spec * rec.kr;                                 // :940
+        }
+        storeSlot(slots, rec.dest, c);
+    }
+}
+
 // Level `level`'s records are [max(interiorEnd of the shallower levels), interiorEnd[level]): levels run one
 // after the other and records are bump-allocated, so each level owns one contiguous range.
 __global__ void k_combine(const Interior* __restrict__ interiors, const LevelCtr* __restrict__ lv, int level, int interiorCap,
@@ -808,21 +943,7 @@ __global__ void k_combine(const Interior* __restrict__ interiors, const LevelCtr
     int first = 0;
     for (int j = 0; j < level; ++j) first = max(first, lv[j].interiorEnd);
     const int last = min(max(first, lv[level].interiorEnd), interiorCap);
-    for (int i = first + blockIdx.x * blockDim.x + threadIdx.x; i < last; i += gridDim.x * blockDim.x) {
-        const Interior rec = interiors[i];
-        const V3 spec = mk(rec.sx, rec.sy, rec.sz);
-        V3 c;
-        if (rec.kind == 1) {
-            c = loadSlot(slots, rec.child) * 0.8f;                 // hitColor = 0.8f * castRay(...)   (:858)
-            c = c + spec;                                          // hitColor += specularComponent    (:890)
-        } else {
-            c = mk(0.0f, 0.0f, 0.0f);                              // hitColor = { 0 }                 (:896)
-            if (rec.kind == 2) c = c + loadSlot(slots, rec.child) * (1 - rec.kr);   // :902
-            c = c + loadSlot(slots, rec.child + 1) * rec.kr;       // :908
-            c = c + spec * rec.kr;                                 // :940
-        }
-        storeSlot(slots, rec.dest, c);
-    }
+    combineStage(interiors, first, last, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, Slots{ slots, nullptr }, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -892,12 +1013,15 @@ __global__ void __launch_bounds__(kBlock) k_sobel(int width, int height, const f
         if (interior) {
             // val = sqrtf(powf(|Gx|,2) + powf(|Gy|,2)) > 0.5f with |G| = (float)sqrt((double)G.G)  (scene.cpp:565-566,
             // geometry.h:99).  Away from the threshold the float sum of squares decides with a wide margin and the
-            // double-precision square roots and the two powf evaluations are skipped.
+            // double-precision square roots are skipped.
             const float s2 = dot(gx, gx) + dot(gy, gy);
             if (s2 > 0.2501f) flag = true;
             else if (s2 < 0.2499f) flag = false;
             else {
-                flag = sqrtf(powExact(length(gx), 2.0f) + powExact(length(gy), 2.0f)) > 0.5f;
+                // powf(v, 2) is compiled to v * v: GCC expands pow with the exponents -1, 0, 1, 2 inline at every
+                // optimisation level (no libm call in the reference binary's launchSSAA), unlike castRay's powf(x, nSpecular)
+                const float lx = length(gx), ly = length(gy);
+                flag = sqrtf(lx * lx + ly * ly) > 0.5f;
             }
             pix = y * width + x;
         }

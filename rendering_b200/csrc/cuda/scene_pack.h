@@ -57,8 +57,58 @@ struct FastPath {
     std::vector<int2> triRefs;       // (reference leaf node, slot), ascending slot per triangle
     std::vector<int> parent;         // reference-tree parents
     int maxDepth = 0;
+    int topNodes = 0;                // nodes [0, topNodes) are the tree's top levels in breadth-first order
     float pad = 0;
 };
+
+// Renumbers the search BVH so that its top levels come first in breadth-first order (at most `topBudget` nodes: whole
+// levels only), followed by the subtrees below them in the builder's depth-first order.  A prefix of the array is then
+// "the top of the tree" — what the tile kernel stages into shared memory — while deep subtrees keep their locality.
+// Only indices change: child order inside a node, boxes and leaf codes stay, so traversal visits the same nodes.
+inline int reorderTopLevelsFirst(std::vector<rtbvh::Node>& nodes, int topBudget)
+{
+    const int n = (int)nodes.size();
+    if (n <= 1) return n;
+    std::vector<int> order;          // order[newIndex] = oldIndex
+    order.reserve(n);
+    std::vector<int> level{ 0 }, nextLevel;
+    // whole levels while they fit the budget
+    while (!level.empty() && (int)(order.size() + level.size()) <= topBudget) {
+        nextLevel.clear();
+        for (int k : level) {
+            order.push_back(k);
+            if (nodes[k].child0 >= 0) nextLevel.push_back(nodes[k].child0);
+            if (nodes[k].child1 >= 0) nextLevel.push_back(nodes[k].child1);
+        }
+        level.swap(nextLevel);
+    }
+    const int nTop = (int)order.size();
+    // the rest: depth-first below every frontier node, frontier in breadth-first order
+    std::vector<int> stack;
+    for (int root : level) {
+        stack.push_back(root);
+        while (!stack.empty()) {
+            const int k = stack.back();
+            stack.pop_back();
+            order.push_back(k);
+            if (nodes[k].child1 >= 0) stack.push_back(nodes[k].child1);
+            if (nodes[k].child0 >= 0) stack.push_back(nodes[k].child0);
+        }
+    }
+    std::vector<int> newIndex(n, -1);
+    for (int i = 0; i < (int)order.size(); ++i) newIndex[order[i]] = i;
+    std::vector<rtbvh::Node> out(order.size());
+    for (int i = 0; i < (int)order.size(); ++i) {
+        rtbvh::Node nd = nodes[order[i]];
+        if (nd.child0 >= 0) nd.child0 = newIndex[nd.child0];
+        if (nd.child1 >= 0) nd.child1 = newIndex[nd.child1];
+        out[i] = nd;
+    }
+    nodes.swap(out);
+    return nTop;
+}
+
+constexpr int kTopLevelBudget = 2048;   // nodes of the breadth-first prefix (128 KB): what shared memory can hold next to the stacks
 
 inline void packFastPath(const RtbMesh& m, FastPath& out)
 {
@@ -79,6 +129,7 @@ inline void packFastPath(const RtbMesh& m, FastPath& out)
     if (const char* e = std::getenv("RTB_BVH_LEAF")) maxLeaf = std::atoi(e);   // tuning knob
     rtbvh::Result bvh = builder.build(m.pos, m.nTris, out.pad, maxLeaf);
     out.maxDepth = bvh.maxDepth;
+    out.topNodes = reorderTopLevelsFirst(bvh.nodes, kTopLevelBudget);
     out.nodes.swap(bvh.nodes);
     out.tris.resize(bvh.triOrder.size() * 3);
     for (size_t k = 0; k < bvh.triOrder.size(); ++k) {

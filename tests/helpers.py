@@ -26,6 +26,8 @@ def oracle():
         lib = C.CDLL(os.path.join(ROOT, "oracle", "_build", "librtb_oracle.so"))
         lib.rtb_oracle_render.argtypes = [C.POINTER(_ffi.RtbScene), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         lib.rtb_oracle_render.restype = C.c_int
+        lib.rtb_oracle_render_sequential.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        lib.rtb_oracle_render_sequential.restype = C.c_int
         lib.rtb_oracle_trace.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         lib.rtb_oracle_cast.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_int, C.c_void_p]
         lib.rtb_oracle_show_ac.argtypes = [C.POINTER(_ffi.RtbScene), C.c_void_p, C.c_void_p]
@@ -53,6 +55,17 @@ def oracle_render(scene, threads=None):
     fin = np.zeros((h, w, 3), np.float32)
     cnt = (C.c_uint64 * 4)()
     rc = oracle().rtb_oracle_render(scene.view, threads or os.cpu_count() or 1, p1.ctypes.data, fin.ctypes.data, cnt)
+    assert rc == 0
+    return p1, fin, dict(zip(["rays", "boxTests", "triTests", "ssaaPixels"], [int(c) for c in cnt]))
+
+
+def oracle_render_sequential(scene):
+    """The frame exactly as the reference renders it with n_workers=1 (tile order, stateful normal maps)."""
+    h, w = scene.height, scene.width
+    p1 = np.zeros((h, w, 3), np.float32)
+    fin = np.zeros((h, w, 3), np.float32)
+    cnt = (C.c_uint64 * 4)()
+    rc = oracle().rtb_oracle_render_sequential(scene.view, p1.ctypes.data, fin.ctypes.data, cnt)
     assert rc == 0
     return p1, fin, dict(zip(["rays", "boxTests", "triTests", "ssaaPixels"], [int(c) for c in cnt]))
 

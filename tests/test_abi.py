@@ -34,7 +34,7 @@ def test_cuda_library_loads_and_exports():
     for name in _ffi.CUDA_SYMBOLS:
         assert hasattr(lib, name), name
     lib.rtb_abi_version.restype = C.c_int
-    assert lib.rtb_abi_version() == 1
+    assert lib.rtb_abi_version() == 2
     lib.rtb_strip_rows_owned.restype = C.c_int
     assert lib.rtb_strip_rows_owned(1080, 32, 0, 8) + lib.rtb_strip_rows_owned(1080, 32, 7, 8) > 0
 

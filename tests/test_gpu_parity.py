@@ -2,10 +2,9 @@
 (oracle/rtb_oracle.c) on the same inputs, against the committed golden fixtures of the reference,
 and through size-independent properties at full size.
 
-Tolerances: Diffuse-only scenes (cfg2, dragon) and showNormals renders must be BIT-EXACT.  Scenes with
-a specular term (Phong / Reflective / Transparent) may differ only where pow() evaluated in double and
-rounded once differs from glibc powf: <= 1e-4 per-channel RMS (north star), and in practice <= 1 ulp
-on < 0.1 % of the pixels — both asserted."""
+Tolerance: NONE.  Every frame must be BIT-EXACT — Diffuse scenes always were; scenes with a specular term (Phong /
+Reflective / Transparent) are too since the kernels evaluate the reference's powf with glibc's own algorithm
+(rt_device.cuh powfGlibc, pinned by tests/test_powf.py).  The north star's 1e-4 RMS allowance is not used."""
 import hashlib
 
 import numpy as np
@@ -20,7 +19,7 @@ from helpers import (GOLDEN, GOLDEN_DIR, HAVE_ASSETS, MIXED_SCENE, MULTI_MESH_SC
 
 pytestmark = pytest.mark.gpu
 
-RMS_TOL = 1e-4
+RMS_TOL = 0.0   # bit-exact: kept as a name for the few comparisons written as an RMS
 
 
 def _skip_if_no_assets(cfg):
@@ -43,11 +42,7 @@ def check_against_oracle(sc, exact, counters=True):
             assert st["boxTests"] == ocnt["boxTests"] and st["triTests"] == ocnt["triTests"]
         for a, b in ((p1, o1), (fb, ofin)):
             d = diff_stats(a, b)
-            if exact:
-                assert d["pixels_differing"] == 0, d
-            else:
-                assert d["rms"] <= RMS_TOL, d
-                assert d["max_abs"] <= 2.5e-7 and d["pixels_differing"] <= 1e-3 * a.shape[0] * a.shape[1], d
+            assert d["pixels_differing"] == 0, (d, exact)
         results.append((fb, p1, st))
     if len(results) == 2:
         assert np.array_equal(results[0][0].view(np.uint32), results[1][0].view(np.uint32))
@@ -59,7 +54,7 @@ def check_against_oracle(sc, exact, counters=True):
 def test_small_configs_vs_oracle_and_golden(name):
     g, sc, data = golden_case(name)
     _skip_if_no_assets(g["scene"])
-    exact = name in ("cfg2_128", "cfgD_160")
+    exact = True
     fb, p1, st = check_against_oracle(sc, exact)
     assert st["rays"] == g["rays"] and st["boxTests"] == g["box_tests"] and st["triTests"] == g["tri_tests"]
     # and directly against the reference's own framebuffers
@@ -79,12 +74,33 @@ def test_full_size_configs_vs_oracle(cfg, exact):
     fb, p1, st = check_against_oracle(sc, exact)
     g = GOLDEN[{"cfg2_smooth_shading_1024": "cfg2_1024", "cfg3_reflective_refractive_1080": "cfg3_1080", "cfg4_shotgun_1080": "cfg4_1080"}[cfg]]
     assert st["rays"] == g["rays"] and st["boxTests"] == g["box_tests"] and st["triTests"] == g["tri_tests"]
-    if exact:
-        assert hashlib.sha256(fb.tobytes()).hexdigest() == g["final_sha256"]
-    else:
-        assert abs(float(fb.astype(np.float64).sum()) - g["final_sum"]) < 1e-3 * abs(g["final_sum"]) * 1e-3
+    assert hashlib.sha256(p1.tobytes()).hexdigest() == g["pass1_sha256_stateless"]
+    # the reference's digest, except where its normal maps' in-place normalisation (objects.cpp:148) makes a re-fetched texel
+    # drift (cfg4: 2 747 pixels; attributed exactly by tests/test_oracle.py): there the stateless digest is the pin
+    assert hashlib.sha256(fb.tobytes()).hexdigest() == g["final_sha256_stateless"]
     # quirks of the reference the frame must keep: last row / column never rendered (scene.cpp:369-372)
     assert not fb[-1].any() and not fb[:, -1].any()
+
+
+@pytest.mark.parametrize("name", ["cfgD_1080", "cfg5_2160"])
+def test_target_configs_at_full_size_vs_reference_digests(name):
+    # the two configs the north star's target sentence is about, pinned to the unmodified reference at full size: pass-1 and
+    # final framebuffer digests, ray count, and (counting handle) the reference's own 32-bit box / triangle test counters
+    g, sc, _ = golden_case(name)
+    _skip_if_no_assets(g["scene"])
+    r = rb.Renderer(sc)
+    fb, p1, st = r.render(want_pass1=True)
+    r.close()
+    assert st["rays"] == g["rays"]
+    assert hashlib.sha256(p1.tobytes()).hexdigest() == g["pass1_sha256_stateless"]
+    assert hashlib.sha256(fb.tobytes()).hexdigest() == g["final_sha256_stateless"]
+    if name == "cfgD_1080":
+        assert g["final_sha256_stateless"] == g["final_sha256"]      # no normal map: the reference's digest itself
+    rc = rb.Renderer(sc, counters=True)
+    fc, sc_ = rc.render()
+    rc.close()
+    assert np.array_equal(fc.view(np.uint32), fb.view(np.uint32))
+    assert (sc_["boxTests"] & 0xffffffff) == g["box_tests"] and (sc_["triTests"] & 0xffffffff) == g["tri_tests"]
 
 
 def test_cfg5_4k_frame_vs_oracle_and_partition_properties():
@@ -97,7 +113,7 @@ def test_cfg5_4k_frame_vs_oracle_and_partition_properties():
     _, ofin, ocnt = oracle_render(sc)
     assert st["rays"] == ocnt["rays"] and st["ssaaPixels"] == ocnt["ssaaPixels"]
     d = diff_stats(fb, ofin)
-    assert d["rms"] <= RMS_TOL and d["max_abs"] <= 2.5e-7 and d["pixels_differing"] <= 1e-3 * fb.shape[0] * fb.shape[1], d
+    assert d["pixels_differing"] == 0, d
     assert not fb[-1].any() and not fb[:, -1].any()
     from rendering_b200 import dist as rdist
     frame = np.zeros_like(fb)
@@ -107,6 +123,41 @@ def test_cfg5_4k_frame_vs_oracle_and_partition_properties():
     assert np.array_equal(frame.view(np.uint32), fb.view(np.uint32))
     again, _ = r.render()
     assert np.array_equal(again.view(np.uint32), fb.view(np.uint32))
+
+
+TILE_VS_WAVEFRONT = ["cfg1_256", "cfg3_240", "cfg4_240", "cfgD_160", "mixed", "multi_mesh"]
+
+
+@pytest.mark.parametrize("name", TILE_VS_WAVEFRONT)
+def test_tile_pipeline_equals_frame_wide_pipeline(name):
+    # default handle = tile pipeline (whole recursion per tile inside k_tile); RTB_CREATE_WAVEFRONT = one launch per stage and
+    # level over frame-wide queues.  Same stage code, different scheduling: frames, pass-1 frames and every counter must agree.
+    if name == "mixed":
+        sc = rb.Scene(text=MIXED_SCENE)
+    elif name == "multi_mesh":
+        if not HAVE_ASSETS:
+            pytest.skip("scenes/input assets not present")
+        sc = rb.Scene(text=MULTI_MESH_SCENE, asset_dir=rb.SCENES_DIR)
+    else:
+        g, sc, _ = golden_case(name)
+        _skip_if_no_assets(g["scene"])
+    a = rb.Renderer(sc)
+    b = rb.Renderer(sc, wavefront=True)
+    fa, pa, sa = a.render(want_pass1=True)
+    fb, pb, sb = b.render(want_pass1=True)
+    assert np.array_equal(fa.view(np.uint32), fb.view(np.uint32)) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+    for k in ("rays", "primaryRays", "secondaryRays", "shadowRays", "ssaaPixels", "shadowRaysSkipped", "levels", "backgroundPixels"):
+        assert sa[k] == sb[k], (k, sa[k], sb[k])
+    assert sa["kernelLaunches"] < sb["kernelLaunches"] and sa["kernelLaunches"] <= 6
+    # strips and a second frame on the same handle
+    part, _ = a.render(7, min(31, sc.height))
+    assert np.array_equal(part.view(np.uint32), fa[7:min(31, sc.height)].view(np.uint32))
+    again, _ = a.render()
+    assert np.array_equal(again.view(np.uint32), fa.view(np.uint32))
+    rng = np.random.default_rng(11)
+    rays = np.concatenate([rng.normal(size=(3000, 3)).astype(np.float32) * np.float32(0.2),
+                           (rng.normal(size=(3000, 3)) * [0.3, 0.3, 0.1] + [0, 0, -1]).astype(np.float32)], 1)
+    assert np.array_equal(a.cast(rays).view(np.uint32), b.cast(rays).view(np.uint32))
 
 
 def test_default_handle_equals_counting_handle():
@@ -468,4 +519,4 @@ def test_trace_and_cast_queries_vs_oracle():
         rgb = r.cast(rays)
         orgb = oracle_cast(sc, rays)
         d_ = diff_stats(rgb, orgb)
-        assert d_["rms"] <= RMS_TOL and d_["max_abs"] <= 5e-7, d_
+        assert d_["pixels_differing"] == 0, d_

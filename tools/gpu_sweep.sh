@@ -1,18 +1,10 @@
 #!/bin/bash
-# tools/gpu_sweep.sh TAG "<env assignments> | <nvcc extra flags>" ... : per configuration rebuild librtb_cuda.so on the
-# GPU box with the flags, export the env assignments, check parity on two small scenes and bench cfg4 + dragon.
-TAG=$1; shift
-mkdir -p gpurun_out
-for CFG in "$@"; do
-  ENVS="${CFG%%|*}"; FL="${CFG#*|}"
-  RTB_NVCC_EXTRA="$FL" python -c "from rendering_b200 import build; build.build_cuda(True)" > /dev/null 2>&1
-  ( export $ENVS
-    python -m pytest tests/test_gpu_parity.py -x -q -k "small_configs or trace_and_cast" 2>&1 | tail -1 | tee -a gpurun_out/${TAG}_sweep.txt
-    for SC in cfg4_shotgun_1080 cfgD_dragon_1080; do
-      python bench.py --steps 30 --warmup 3 --scene $SC --no-cpu-baseline 2>/dev/null | python -c "
-import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1])
-print('[$CFG]', '$SC', 'ms', round(d['ms_per_step'], 4), 'e2e_ms', round(d['e2e']['ms_per_step'], 4), {k: round(v, 4) for k, v in d['kernel_ms_per_step'].items() if v})
-" | tee -a gpurun_out/${TAG}_sweep.txt
-    done )
+# experiment sweep on the GPU box: tile-pipeline variants (group width / CTAs per SM / tile size) on the main configs
+cd "$(dirname "$0")/.."
+CFGS="cfg1_simple_shapes_256 cfg3_reflective_refractive_1080 cfg4_shotgun_1080 cfgD_dragon_1080"
+for lib in default t256b3 t128b8 t128b6; do
+  for R in 0 256 512 1024; do
+    if [ $lib = default ]; then unset RTB_CUDA_LIB; else export RTB_CUDA_LIB=$PWD/build_variants/librtb_cuda_$lib.so; fi
+    RTB_TILE_RAYS=$R RTB_AB_TAG=sweep_${lib}_R$R timeout 300 python tools/gpu_ab.py --tile-only $CFGS 2>&1 | grep SUMMARY
+  done
 done
