@@ -13,16 +13,19 @@ ours:       value  = rays / device time, scene and queues resident in HBM, frame
             e2e    = the same frame through the public host-buffer call Scene::render() makes
                      (rtb_render_bgr8 into pinned HOST memory: the frame arrives as the BMP's pixel
                      bytes, D2H inside the call); e2e_float = rtb_render with a float32 host framebuffer.
-            roofline = the dominant traversal kernel (k_walk closest-hit or shadow), algorithmic bytes
-                     from the reference's own work counts: 48 B/ray + 32 B/box test +
-                     48 B/triangle test, over its CUDA-event time measured on a handle created with
-                     RTB_CREATE_KERNEL_TIMING over the same frames (per-launch events cost stream
-                     time, so `value` is taken on a handle without them).
+            roofline = the dominant kernel (k_tile, pass 1): frac = PHYSICAL DRAM bytes per launch (ncu capture at
+                     HEAD, profiles/traffic.json) over its live CUDA-event time (handle created with
+                     RTB_CREATE_KERNEL_TIMING) against the measured HBM peak; roofline.issue = the issue-slot
+                     roofline that actually binds it; roofline.work_normalised = SURVEY.md 8d's yardstick
+                     (reference work counts), reported but not a roofline fraction.
+            parity_sha_ok = sha256 of the last timed frame equals the committed golden digest.
 reference:  oracle/_ref/ref_driver (the unmodified reference sources, compiled by oracle/Makefile)
             timing launchWorkers + launchSSAA on all host cores; the oracle port when that binary
             is absent.
-N > 1:      rows are dealt to ranks in cyclic strips, each rank renders its strips, one
-            torch.distributed gather (NCCL) assembles the frame on rank 0; strong scaling.
+N > 1:      rows are dealt to ranks in cyclic strips (counted from the first row that can contain geometry), each rank
+            renders its strips and its output kernel stores them over NVLink straight into rank 0's double-buffered
+            symmetric-memory frame, one device-side barrier closes the frame (--transport nccl: one NCCL gather instead);
+            strong scaling.
 """
 from __future__ import annotations
 
@@ -40,7 +43,8 @@ sys.path.insert(0, ROOT)
 METRIC = "Mrays/s"
 DEFAULT_SCENE = "cfg4_shotgun_1080"
 GOLDEN_KEY = {"cfg4_shotgun_1080": "cfg4_1080", "cfg2_smooth_shading_1024": "cfg2_1024",
-              "cfg3_reflective_refractive_1080": "cfg3_1080", "cfg1_simple_shapes_256": "cfg1_256"}
+              "cfg3_reflective_refractive_1080": "cfg3_1080", "cfg1_simple_shapes_256": "cfg1_256",
+              "cfg5_shotgun_2160": "cfg5_2160", "cfgD_dragon_1080": "cfgD_1080"}
 L2_FLUSH_BYTES = 256 << 20
 
 
@@ -101,6 +105,18 @@ def run_reference(scene, frames, warmup, rays):
                 "sample": f"{len(ms)} full frames of {scene}, oracle/rtb_oracle.c with {cores} pthreads"}
 
 
+def scene_size(scene):
+    """width, height of a bundled config scene (from its [options] block), without loading any asset"""
+    w = h = None
+    for ln in open(os.path.join(ROOT, "scenes", scene + ".scene")):
+        ln = ln.strip()
+        if ln.startswith("width="):
+            w = int(ln.split("=")[1])
+        elif ln.startswith("height="):
+            h = int(ln.split("=")[1])
+    return w, h
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -120,7 +136,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": mean_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "reference assets (scenes/input), no randomness",
-        "config": {"workload": f"{args.scene}: 1920x1080 frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays},
+        "config": workload_config(args.scene, *scene_size(args.scene), rays),
         "cpu_baseline": dict(info, value=value, unit="Mrays/s"),
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -172,7 +188,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------
+def workload_config(scene, w, h, rays):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": f"{scene}: {w}x{h} frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays}
+
+
 def ours(args):
+    import hashlib
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -191,35 +213,37 @@ def ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    sc = rb.Scene(rb.scene_path(args.scene))
+    t0 = time.perf_counter()
+    sc = rb.Scene(rb.scene_path(args.scene))          # .scene / .obj / .bmp loaders + reference tree build (host)
+    load_ms = (time.perf_counter() - t0) * 1e3
     h, w = sc.height, sc.width
     stream = torch.cuda.Stream()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
-    # reference-defined work of the frame, per kernel kind (outside the timed region)
+    # reference-defined work of the frame (outside the timed region): the literal reference walk with counters
     counted = rb.Renderer(sc, device=local, counters=True)
     _, cst = counted.render()
     counted.close()
     rays = cst["rays"]
-    closest_rays = cst["primaryRays"] + cst["secondaryRays"]
-    trace_bytes = 48 * closest_rays + 32 * (cst["boxTests"] - cst["boxTestsShadow"]) + 48 * (cst["triTests"] - cst["triTestsShadow"])
-    shadow_bytes = 48 * cst["shadowRays"] + 32 * cst["boxTestsShadow"] + 48 * cst["triTestsShadow"]
+    yardstick_bytes = 48 * rays + 32 * cst["boxTests"] + 48 * cst["triTests"] + 12 * w * h      # SURVEY.md 8d, whole frame
 
     # the fast path's OWN work for the same frame (search-BVH nodes fetched, triangles tested), also untimed
     wst_r = rb.Renderer(sc, device=local, walk_stats=True)
     _, wst = wst_r.render()
     wst_r.close()
-    own_bytes = [64 * wst["walkNodes"][k] + 48 * wst["walkTris"][k] + 64 * wst["walkEligibility"][k] for k in (0, 1)]
-    own_bytes[0] += 48 * closest_rays
-    own_bytes[1] += 48 * cst["shadowRays"]
+    own_bytes = sum(64 * wst["walkNodes"][k] + 48 * wst["walkTris"][k] + 64 * wst["walkEligibility"][k] for k in (0, 1)) + 48 * rays
 
-    r = rb.Renderer(sc, device=local)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = rb.Renderer(sc, device=local)                  # upload + search-BVH build + eligibility tables (rtb_create)
+    create_ms = (time.perf_counter() - t0) * 1e3
     out = torch.empty((h, w, 3), dtype=torch.float32, device="cuda") if world == 1 else None
-    exchange = rdist.FrameExchange(h, w, args.strip_rows, rank, world, torch.device("cuda", local), args.transport) if world > 1 else None
+    exchange = (rdist.FrameExchange(h, w, args.strip_rows, rank, world, torch.device("cuda", local), args.transport, origin=r.strip_origin())
+                if world > 1 else None)
 
     def step(rr):
         if world == 1:
-            return rr.render_device(out.data_ptr(), stream=stream.cuda_stream), None
+            return rr.render_device(out.data_ptr(), stream=stream.cuda_stream), out
         return exchange.render(rr, stream)
 
     def barrier():
@@ -233,6 +257,7 @@ def ours(args):
         total, launches = 0.0, 0
         kms = [0.0] * len(KERNEL_KINDS)
         kl = [0] * len(KERNEL_KINDS)
+        last = None
         barrier()
         for _ in range(steps):
             with torch.cuda.stream(stream):
@@ -240,7 +265,7 @@ def ours(args):
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            st, _ = step(rr)
+            st, last = step(rr)
             e1.record(stream)
             e1.synchronize()
             total += e0.elapsed_time(e1)
@@ -249,7 +274,7 @@ def ours(args):
                 kms[k] += st["msKernel"][k]
                 kl[k] += st["launchesKernel"][k]
         barrier()
-        return total, launches, kms, kl
+        return total, launches, kms, kl, st, last
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -258,7 +283,7 @@ def ours(args):
 
     sampler = ClockSampler(local)
     with sampler:
-        total_ms, launches, _, _ = timed_loop(r, args.steps)
+        total_ms, launches, _, _, fst, last_frame = timed_loop(r, args.steps)
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -266,51 +291,68 @@ def ours(args):
         ms_per_step = total_ms / args.steps
         value = rays / (ms_per_step * 1e-3) / 1e6
 
+        # ---- parity of the frame just timed: sha256 of the last timed frame against the committed golden digest ----
+        parity = None
+        if rank == 0:
+            digest = hashlib.sha256(last_frame.cpu().numpy().tobytes()).hexdigest()
+            try:
+                g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))[GOLDEN_KEY[args.scene]]
+                parity = {"frame_sha256": digest, "golden": "tests/golden/golden.json:" + GOLDEN_KEY[args.scene],
+                          "ok": digest == g["final_sha256_stateless"], "equals_reference_digest": digest == g["final_sha256"],
+                          "pixels_where_the_reference_differs": g.get("stateful_pixels", 0),
+                          "note": "golden = digest of the unmodified reference's framebuffer (oracle/_ref, tests/golden/make_golden.py); where a "
+                                  "normal-map texel is fetched twice the reference's in-place normalisation (objects.cpp:148) drifts by an ulp and the pin "
+                                  "is the stateless digest, attributed pixel for pixel by tests/test_oracle.py"}
+            except Exception as e:   # noqa: BLE001
+                parity = {"frame_sha256": digest, "ok": None, "note": f"no golden digest: {e}"}
+
         # ---- per-kernel durations: the same frames on a handle that brackets every launch with CUDA events
         #      (RTB_CREATE_KERNEL_TIMING; the events themselves cost stream time, so `value` is taken without them)
         rt_ = rb.Renderer(sc, device=local, kernel_timing=True)
         for _ in range(warm):
             step(rt_)
         ksteps = min(args.steps, 50)
-        ktotal_ms, _, kernel_ms, kernel_launches = timed_loop(rt_, ksteps)
+        ktotal_ms, _, kernel_ms, kernel_launches, _, _ = timed_loop(rt_, ksteps)
         rt_.close()
 
         # ---- end to end through the public host-buffer calls --------------------------------------
         # headline: rtb_render_bgr8, what Scene::render() calls (the frame arrives as the BMP's pixel bytes);
-        # also reported: rtb_render with a float32 host framebuffer (4x the bytes over PCIe)
+        # also reported: rtb_render with a float32 host framebuffer (4x the bytes over PCIe).
+        # N > 1: no host-level barrier between frames — the exchange's device-side barrier is the only synchronisation.
         row_bytes = (w * 3 + 3) & ~3
         host_px = torch.empty((h, row_bytes), dtype=torch.uint8).pin_memory()
         host_fb = torch.empty((h, w, 3), dtype=torch.float32).pin_memory()
         e2e = {}
         for name in ("bgr8", "float"):
-            e2e_ms = 0.0
             h2d = d2h = 0
-            for i in range(args.steps + 2):
-                barrier()
-                t0 = time.perf_counter()
+
+            def frame():
                 # the step's input is the camera: uploaded (host -> device) inside the timed region, as a frame loop does
                 r.set_camera_raw(sc.desc.camera)
                 if world == 1:
+                    _, est = r.render_bgr8(out=host_px.numpy()) if name == "bgr8" else r.render(out=host_fb.numpy())
+                    return est["h2dBytes"], est["d2hBytes"]
+                est, fr = step(r)
+                extra = 0
+                if rank == 0:
                     if name == "bgr8":
-                        _, est = r.render_bgr8(out=host_px.numpy())
+                        r.frame_to_bgr8(fr.data_ptr(), host_px.numpy(), stream=stream.cuda_stream)
+                        extra = host_px.numel()
                     else:
-                        _, est = r.render(out=host_fb.numpy())
-                    h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
-                else:
-                    est, frame = step(r)
-                    h2d_i, d2h_i = est["h2dBytes"], est["d2hBytes"]
-                    if rank == 0:
+                        with torch.cuda.stream(stream):
+                            host_fb.copy_(fr, non_blocking=True)
                         stream.synchronize()
-                        if name == "bgr8":
-                            r.frame_to_bgr8(frame.data_ptr(), host_px.numpy())
-                            d2h_i += host_px.numel()
-                        else:
-                            host_fb.copy_(frame, non_blocking=False)
-                            d2h_i += host_fb.numel() * 4
-                barrier()
-                if i > 1:
-                    e2e_ms += (time.perf_counter() - t0) * 1e3
-                    h2d, d2h = h2d_i, d2h_i
+                        extra = host_fb.numel() * 4
+                return est["h2dBytes"], est["d2hBytes"] + extra
+
+            for _ in range(2):
+                frame()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                h2d, d2h = frame()
+            barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
             te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -330,53 +372,62 @@ def ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    k_trace = KERNEL_KINDS.index("trace")
-    k_shadow = KERNEL_KINDS.index("shadow")
-    dom = k_trace if kernel_ms[k_trace] >= kernel_ms[k_shadow] else k_shadow
-    dom_bytes = (trace_bytes if dom == k_trace else shadow_bytes) / max(1, world)   # per rank share, approx. for N>1
+    k_tile, k_ssaa = KERNEL_KINDS.index("tile"), KERNEL_KINDS.index("tile_ssaa")
+    dom, dom_name = (k_tile, "k_tile") if kernel_ms[k_tile] >= kernel_ms[k_ssaa] else (k_ssaa, "k_tile_ssaa")
     dom_launches = max(1, kernel_launches[dom])
-    launches_per_step = dom_launches / ksteps
     avg_launch_ms = kernel_ms[dom] / dom_launches
-    achieved = (dom_bytes / launches_per_step) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
-    traffic = None
-    try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr[args.scene]["k_" + KERNEL_KINDS[dom]]["dram_bytes_per_launch"]
+    tile_ms_per_frame = (kernel_ms[k_tile] + kernel_ms[k_ssaa]) / ksteps
+    prof = {}
+    try:   # physical DRAM bytes and issue statistics per launch from the committed ncu --set full capture (profiles/traffic.json)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.scene][dom_name]
     except Exception:
         pass
-
-    kdom = 0 if dom == k_trace else 1
-    own = own_bytes[kdom] / max(1, world)
-    own_achieved = (own / launches_per_step) / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
-    head = e2e["bgr8"] if e2e.get("bgr8") else e2e["float"]
+    traffic = prof.get("dram_bytes_per_launch")
+    traffic_rank = traffic / max(1, world) if traffic else None           # per rank share, approx. for N>1
+    achieved = traffic_rank / (avg_launch_ms * 1e-3) / 1e9 if traffic_rank and avg_launch_ms > 0 else None
+    issue = dict(prof.get("issue", {}))
+    if issue and avg_launch_ms > 0:
+        # issue-slot roofline: warp instructions of the launch / (148 SMs x 4 schedulers x SM clock) over the LIVE launch time
+        issue["frac_of_issue_peak_live"] = issue["inst_executed"] / max(1, world) / (148 * 4 * 1.965e9) / (avg_launch_ms * 1e-3)
+    traced = rays - fst["shadowRaysSkipped"] - fst["backgroundPixels"] if world == 1 else None
+    head = e2e["bgr8"]
     line = {
         "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference assets (scenes/input), no randomness",
-        "config": {"workload": f"{args.scene}: {w}x{h} frame, pass 1 + Sobel + 4x SSAA re-trace", "rays_per_frame": rays,
-                   "l2": "flushed between timed frames (256 MiB write)", "partition": (f"cyclic strips of {args.strip_rows} rows; exchange: " + ("NVLink stores into rank 0's symmetric-memory frame + 1 device barrier" if exchange.transport == "p2p" else "1 NCCL gather")) if world > 1 else "single GPU",
-                   "timing": "CUDA events on the render stream per frame, summed; max over ranks"},
+        "config": workload_config(args.scene, w, h, rays),
+        "method": {"l2": "flushed between timed frames (256 MiB write)",
+                   "partition": (f"cyclic strips of {args.strip_rows} rows counted from the first geometry row; exchange: "
+                                 + ("NVLink stores into rank 0's double-buffered symmetric-memory frame + 1 device barrier" if exchange.transport == "p2p" else "1 NCCL gather"))
+                   if world > 1 else "single GPU",
+                   "timing": "CUDA events on the render stream per frame, summed; max over ranks",
+                   "pipeline": "tile (k_tile: whole recursion per 256-ray tile inside one persistent kernel per pass)"},
+        "parity_sha_ok": parity["ok"] if parity else None, "parity": parity,
+        "rays": {"reference_equivalent": rays, "note": "numerator of value / e2e: the reference's Render::trace call count for this frame (SURVEY.md 8d)",
+                 "traced": traced, "background_prefilled_primaries": fst["backgroundPixels"] if world == 1 else None,
+                 "dead_shadow_rays_not_traced": fst["shadowRaysSkipped"] if world == 1 else None,
+                 "value_traced": traced / (ms_per_step * 1e-3) / 1e6 if traced else None},
         "e2e": dict(head, what=("per frame: camera constants uploaded (rtb_set_camera), rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes), wall clock"
-                                if world == 1 else f"strips rendered per rank, exchanged to rank 0 ({exchange.transport}), converted to BMP pixel bytes there and copied to pinned host memory, wall clock")),
-        "e2e_float": e2e["float"] if e2e.get("bgr8") else None,
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "k_walk (" + ("closest hit" if dom == k_trace else "shadow / any hit") + ")",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom_bytes / launches_per_step, "avg_launch_ms": avg_launch_ms,
-                     "launches_per_step": launches_per_step,
-                     "own_work": {"bytes_per_launch": own / launches_per_step, "achieved": own_achieved, "unit": "GB/s",
-                                  "frac_of_hbm_peak": own_achieved / peak if peak else None,
-                                  "nodes_fetched": wst["walkNodes"][kdom], "triangles_tested": wst["walkTris"][kdom],
-                                  "eligibility_evaluations": wst["walkEligibility"][kdom],
-                                  "note": "what THIS kernel's algorithm touches: 64 B per search-BVH node fetched + 48 B per triangle "
-                                          "tested + 64 B per eligibility evaluation + 48 B per ray; served almost entirely from L1/L2 "
-                                          "(see traffic for the DRAM share), so it is a cache-bandwidth figure quoted against the HBM peak"},
-                     "note": "bytes = 48/ray + 32/box test + 48/triangle test with the REFERENCE's work counts (SURVEY.md 8d): a work-"
-                             "normalised yardstick, not DRAM traffic (the fast path tests ~1/100 of the reference's triangles and the "
-                             "geometry is L2-resident), hence frac > 1; durations from a handle with per-launch CUDA events "
-                             f"({ksteps} frames, {ktotal_ms / ksteps:.4f} ms/frame with the events)"},
-        "kernel_ms_per_step": {KERNEL_KINDS[k]: kernel_ms[k] / ksteps for k in range(len(KERNEL_KINDS))},
+                                if world == 1 else f"per frame: camera uploaded on every rank, strips rendered, exchanged to rank 0 ({exchange.transport}), converted to BMP pixel bytes there and copied to pinned host memory; wall clock over all frames, no host barrier between frames")),
+        "e2e_float": e2e["float"],
+        "gpu_launches": launches, "launches_per_frame": launches / args.steps,
+        "roofline": {"bound": "hbm", "kernel": dom_name + (" (pass 1: ray generation, traversal, surface, shadow, shade of every tile)" if dom == k_tile else " (SSAA samples)"),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved and peak else None,
+                     "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_launch_ms, "launches_per_step": dom_launches / ksteps,
+                     "what": "PHYSICAL: dram__bytes_read+write per launch of that kernel (ncu --set full at HEAD, profiles/traffic.json) over its live CUDA-event "
+                             "duration.  The scene is L1/L2-resident, so the kernel is nowhere near the HBM roof; it is bound by instruction issue (see issue)",
+                     "issue": issue or None,
+                     "work_normalised": {"bytes_per_frame": yardstick_bytes, "achieved": yardstick_bytes / max(1, world) / (tile_ms_per_frame * 1e-3) / 1e9 if tile_ms_per_frame > 0 else None,
+                                         "unit": "GB/s", "over": "both k_tile launches of a frame",
+                                         "note": "SURVEY.md 8d yardstick: 48 B/ray + 32 B/box test + 48 B/triangle test with the REFERENCE's work counts + 12 B/pixel; the fast "
+                                                 "path tests ~1/100 of the reference's triangles, so this exceeds the HBM peak and is NOT a roofline fraction"},
+                     "own_work": {"bytes_per_frame": own_bytes, "achieved": own_bytes / max(1, world) / (tile_ms_per_frame * 1e-3) / 1e9 if tile_ms_per_frame > 0 else None, "unit": "GB/s",
+                                  "nodes_fetched": sum(wst["walkNodes"]), "triangles_tested": sum(wst["walkTris"]), "eligibility_evaluations": sum(wst["walkEligibility"]),
+                                  "note": "what THIS algorithm touches: 64 B per search-BVH node + 48 B per triangle tested + 64 B per eligibility evaluation + 48 B per ray, "
+                                          "served from L1/L2: a cache-bandwidth figure"},
+                     "timing_note": f"per-launch durations from a handle with CUDA events around every launch ({ksteps} frames, {ktotal_ms / ksteps:.4f} ms/frame with the events)"},
+        "kernel_ms_per_step": {KERNEL_KINDS[k]: kernel_ms[k] / ksteps for k in range(len(KERNEL_KINDS)) if kernel_launches[k]},
+        "setup_ms": {"scene_load_host": load_ms, "rtb_create": create_ms, "note": "outside the timed region: loaders + reference tree (host); upload, search BVH, eligibility tables"},
         "clocks": sampler.summary(),
     }
     if args.gpus == 1 and not args.no_cpu_baseline:

@@ -241,8 +241,15 @@ int  rtb_render_strips(RtbHandle* h, int stripRows, int rank, int worldSize, flo
 int  rtb_render_strips_to_frame(RtbHandle* h, int stripRows, int rank, int worldSize, float* frame, void* stream, RtbStats* stats);
 /* saveImage's conversion (see rtb_render_bgr8) of an assembled full float frame resident on the handle's device.    */
 int  rtb_frame_to_bgr8(RtbHandle* h, const float* frame, uint8_t* bgr, int onDevice, void* stream);
-/* Number of rows rank owns under that partition (for sizing buffers).                              */
+/* Number of rows rank owns under that partition with the strips counted from row 0 (for sizing buffers: an upper
+ * bound is ceil(height / (stripRows*worldSize)) * stripRows + stripRows for any origin).                            */
 int  rtb_strip_rows_owned(int height, int stripRows, int rank, int worldSize);
+/* The strips of rtb_render_strips* are counted from the first image row that can contain geometry (so the rows that
+ * cost something are dealt evenly): strip s = floor((y - origin) / stripRows) belongs to rank s mod worldSize.
+ * rtb_strip_origin returns that row for the handle's current camera; rtb_strip_rows lists (rowsOut, may be NULL) and
+ * counts the rows of `rank` for a given origin.                                                                     */
+int  rtb_strip_origin(const RtbHandle* h);
+int  rtb_strip_rows(int height, int stripRows, int origin, int rank, int worldSize, int32_t* rowsOut);
 
 /* Closest-hit query on caller-supplied rays (orig.xyz dir.xyz per ray): the device equivalent of
  * Render::trace (scene.cpp:724-756).  out: per ray {t,u,v} floats and {object,tri} ints (-1 miss). */

@@ -171,8 +171,19 @@ class Renderer:
         self._check(self._lib.rtb_render(self._h, y0, y1, C.c_void_p(dev_ptr), None, 1, C.c_void_p(stream) if stream else None, C.byref(st)))
         return st.as_dict()
 
+    def strip_origin(self) -> int:
+        """First image row that can contain geometry: the cyclic strips of render_strips* are counted from it."""
+        return self._lib.rtb_strip_origin(self._h)
+
     def rows_owned(self, strip_rows: int, rank: int, world: int) -> int:
-        return self._lib.rtb_strip_rows_owned(self.height, strip_rows, rank, world)
+        return self._lib.rtb_strip_rows(self.height, strip_rows, self.strip_origin(), rank, world, None)
+
+    def strip_rows(self, strip_rows: int, rank: int, world: int) -> np.ndarray:
+        """Image rows (ascending) `rank` renders under the handle's strip partition."""
+        n = self.rows_owned(strip_rows, rank, world)
+        rows = np.empty(n, np.int32)
+        self._lib.rtb_strip_rows(self.height, strip_rows, self.strip_origin(), rank, world, rows.ctypes.data)
+        return rows
 
     def render_strips_device(self, dev_ptr: int, strip_rows: int, rank: int, world: int, stream: int | None = None) -> dict:
         st = _ffi.RtbStats()

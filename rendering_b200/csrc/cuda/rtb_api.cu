@@ -84,6 +84,8 @@ struct RtbHandle {
 
     rt::Scene scene{};                 // header with DEVICE pointers
     rt::Scene* sceneDev = nullptr;     // the same header resident in HBM
+    rt::Scene* scenePinned = nullptr;  // pinned staging copy: rtb_set_camera writes it, the next render call uploads it on ITS stream
+    bool sceneDirty = false;
     std::vector<void*> allocations;    // scene-lifetime device allocations
     std::vector<TextureRes> textures;
     bool kernelTiming = false;         // bracket every launch with CUDA events (RTB_CREATE_KERNEL_TIMING -> RtbStats.msKernel)
@@ -114,7 +116,7 @@ struct RtbHandle {
     bool stagedAttrSet[3] = { false, false, false };
 
     QueueBufs rays[2];
-    DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, userRays, outStage;
+    DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, rowsC, userRays, outStage;
     DevBuf ctrBuf;                     // FrameCtr followed by 2 passes x (levels + 1) LevelCtr
     void* hCtr = nullptr;              // pinned mirror of ctrBuf
     size_t ctrBytes = 0;
@@ -128,7 +130,7 @@ struct RtbHandle {
     long long capSlots = 0;
     // SSAA capacity hint carried from frame to frame: flagged pixels seen last time
     long long flaggedSeen = 0;
-    std::vector<int> rowsAHost, rowsBHost;   // row lists currently resident in rowsA / rowsB
+    std::vector<int> rowsAHost, rowsBHost, rowsCHost;   // row lists currently resident in rowsA / rowsB / rowsC
 
     // per-kernel timing: (kind, start, stop) spans recorded on the render stream, resolved at the end of a call
     struct Span { int kind; cudaEvent_t a, b; };
@@ -168,22 +170,25 @@ rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
     rt::Image out{};
     if (!im.rgb || im.width <= 0 || im.height <= 0) return out;
     const size_t nTexels = (size_t)im.width * im.height;
-    // 3 B / texel over PCIe, widened to RGBA8 on the device, then laid out as a CUDA array (2D-local texture fetches)
-    unsigned char* dRgb = nullptr;
-    uchar4* dRgba = nullptr;
-    CK(cudaMalloc((void**)&dRgb, nTexels * 3));
-    CK(cudaMalloc((void**)&dRgba, nTexels * sizeof(uchar4)));
-    CK(cudaMemcpy(dRgb, im.rgb, nTexels * 3, cudaMemcpyHostToDevice));
+    // 3 B / texel over PCIe, widened to RGBA8 on the device, then laid out as a CUDA array (2D-local texture fetches).
+    // Staging buffers are released on every path (a failing call unwinds through here).
+    struct Staging {
+        unsigned char* rgb = nullptr; uchar4* rgba = nullptr;
+        ~Staging() { if (rgb) cudaFree(rgb); if (rgba) cudaFree(rgba); }
+    } stg;
+    cudaStream_t st = h->ownStream;
+    CK(cudaMalloc((void**)&stg.rgb, nTexels * 3));
+    CK(cudaMalloc((void**)&stg.rgba, nTexels * sizeof(uchar4)));
+    CK(cudaMemcpyAsync(stg.rgb, im.rgb, nTexels * 3, cudaMemcpyHostToDevice, st));
     const int blocks = (int)std::min<size_t>((nTexels + 255) / 256, (size_t)h->smCount * 16);
-    rtk::k_rgb_to_rgba<<<blocks, 256>>>(dRgb, nTexels, dRgba);
+    rtk::k_rgb_to_rgba<<<blocks, 256, 0, st>>>(stg.rgb, nTexels, stg.rgba);
     CK(cudaGetLastError());
     TextureRes res;
     const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
     CK(cudaMallocArray(&res.array, &fmt, im.width, im.height));
-    CK(cudaMemcpy2DToArray(res.array, 0, 0, dRgba, (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyDeviceToDevice));
-    CK(cudaDeviceSynchronize());
-    CK(cudaFree(dRgb));
-    CK(cudaFree(dRgba));
+    h->textures.push_back(res);       // owned by the handle from here on (destroyHandle frees it even if a later step throws)
+    CK(cudaMemcpy2DToArrayAsync(res.array, 0, 0, stg.rgba, (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyDeviceToDevice, st));
+    CK(cudaStreamSynchronize(st));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
     rd.res.array.array = res.array;
@@ -193,7 +198,7 @@ rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
     td.readMode = cudaReadModeElementType;        // raw bytes; /256 happens in fetchTexel
     td.normalizedCoords = 0;
     CK(cudaCreateTextureObject(&res.tex, &rd, &td, nullptr));
-    h->textures.push_back(res);
+    h->textures.back().tex = res.tex;
     out.tex = (unsigned long long)res.tex;
     out.rgba = nullptr;
     out.w = im.width;
@@ -490,6 +495,15 @@ void enqueueLevels(RtbHandle* h, cudaStream_t st, int pass, long long framePixel
     }
 }
 
+// A camera set since the last call reaches the device copy of the header here, stream-ordered before the kernels of
+// this call and without a synchronisation (the call itself ends with one, so the staging copy is free again on return).
+void uploadSceneHeader(RtbHandle* h, cudaStream_t st)
+{
+    if (!h->sceneDirty) return;
+    CK(cudaMemcpyAsync(h->sceneDev, h->scenePinned, sizeof(rt::Scene), cudaMemcpyHostToDevice, st));
+    h->sceneDirty = false;
+}
+
 void beginCall(RtbHandle* h)
 {
     CK(cudaSetDevice(h->device));
@@ -576,6 +590,7 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
 {
     cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
     beginCall(h);
+    uploadSceneHeader(h, st);
     const rt::Scene& sc = h->scene;
     const int w = sc.width, ht = sc.height;
     const long long framePixels = (long long)w * ht;
@@ -601,6 +616,17 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     const int genX0 = culled ? rect[0] : 0, genCols = culled ? rect[1] - rect[0] : w - 1;
     uploadRows(h, st, h->rowsA, h->rowsAHost, genRows);
     uploadRows(h, st, h->rowsB, h->rowsBHost, owned);
+    // rows this call initialises: what it renders plus what its Sobel windows read (incl. the never-rendered last row)
+    std::vector<int> initRows;
+    {
+        std::vector<char> need(ht, 0);
+        for (int y : p1rows) need[y] = 1;
+        for (int y : owned)
+            for (int dy = -1; dy <= 1; ++dy)
+                if (y + dy >= 0 && y + dy < ht) need[y + dy] = 1;
+        for (int y = 0; y < ht; ++y) if (need[y]) initRows.push_back(y);
+    }
+    uploadRows(h, st, h->rowsC, h->rowsCHost, initRows);
 
     const long long nPixels = (long long)p1rows.size() * (w - 1);
     const long long n0 = (!genRows.empty() && genCols > 0) ? rtk::raygenPaddedCount(genCols + 1, (int)genRows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
@@ -619,12 +645,12 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
         const int sampleBase = (int)framePixels;
 
         CK(cudaEventRecord(h->ev[0], st));
-        if (culled) {
+        if (!initRows.empty()) {
+            // culled: background colour where a primary ray would miss by construction; else Vec3f() zero-init (scene.cpp:599)
             KernelSpan ks(h, st, RTB_K_RAYGEN);
-            rtk::k_fill_background<<<gridFor(h, framePixels), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, ht, sc.background);
+            rtk::k_fill_background<<<gridFor(h, (long long)initRows.size() * w), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, ht, h->rowsC.as<int>(),
+                (int)initRows.size(), culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f));
             ks.done();
-        } else {
-            CK(cudaMemsetAsync(h->slots.p, 0, (size_t)framePixels * 3 * sizeof(float), st));   // Vec3f() zero-init (scene.cpp:599)
         }
         CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
         if (n0 > 0) {
@@ -733,6 +759,7 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
 void enqueueUserRays(RtbHandle* h, cudaStream_t st, const float* rays, int nRays, bool shade)
 {
     beginCall(h);
+    uploadSceneHeader(h, st);
     for (int attempt = 0;; ++attempt) {
         {
             const bool tileCast = shade && h->tilePipeline;
@@ -775,18 +802,32 @@ int guarded(F&& f)
         g_err = std::string(e.what) + ": " + cudaGetErrorString(e.e);
         cudaGetLastError();
         return e.e == cudaErrorMemoryAllocation ? RTB_ERR_NOMEM : RTB_ERR_CUDA;
+    } catch (const std::invalid_argument& e) {
+        g_err = e.what();
+        return RTB_ERR_ARG;
     } catch (const std::exception& e) {
         g_err = e.what();
         return RTB_ERR_CUDA;
     }
 }
 
-std::vector<int> stripRows(int height, int stripRowsN, int rank, int world)
+// Cyclic strips counted from row `origin` (the first row that can contain geometry): strip s = floor((y - origin) / stripRowsN)
+// belongs to rank s mod world, so the rows that cost something are dealt evenly whatever lies above them.
+std::vector<int> stripRows(int height, int stripRowsN, int rank, int world, int origin)
 {
     std::vector<int> rows;
-    for (int y = 0; y < height; ++y)
-        if ((y / stripRowsN) % world == rank) rows.push_back(y);
+    for (int y = 0; y < height; ++y) {
+        const int d = y - origin;
+        const int s = d >= 0 ? d / stripRowsN : -((-d + stripRowsN - 1) / stripRowsN);
+        if (((s % world) + world) % world == rank) rows.push_back(y);
+    }
     return rows;
+}
+
+int stripOrigin(const RtbHandle* h)
+{
+    const bool literalWalk = h->createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK);
+    return literalWalk ? 0 : std::max(0, std::min(h->primRect[2], h->scene.height - 1));
 }
 
 void destroyHandle(RtbHandle* h)
@@ -800,10 +841,11 @@ void destroyHandle(RtbHandle* h)
     for (void* p : h->allocations) cudaFree(p);
     h->rays[0].release(); h->rays[1].release();
     for (DevBuf* b : { &h->hitTuv, &h->hitObj, &h->surfP, &h->surfN, &h->surfC, &h->vis, &h->interiors, &h->slots, &h->flagged,
-             &h->rowsA, &h->rowsB, &h->userRays, &h->outStage, &h->tileSlab })
+             &h->rowsA, &h->rowsB, &h->rowsC, &h->userRays, &h->outStage, &h->tileSlab })
         b->release();
     h->ctrBuf.release();
     if (h->hCtr) cudaFreeHost(h->hCtr);
+    if (h->scenePinned) cudaFreeHost(h->scenePinned);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->eventPool) cudaEventDestroy(e);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
@@ -903,10 +945,17 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         }
         if (const char* e = getenv("RTB_TILE_STAGED")) h->tileStaged = atoi(e) != 0;
         h->scene.areaPoints = upload(h, s->areaPoints, (size_t)s->nAreaPoints * 3);
-        if (s->flags & RTB_FLAG_USE_SKYBOX)
+        if (s->flags & RTB_FLAG_USE_SKYBOX) {
+            // getSkybox indexes every face with one width / height (scene.cpp:381-442): six faces, all present, one size
+            for (int k = 0; k < 6; ++k)
+                if (!s->skybox[k].rgb || s->skybox[k].width <= 0 || s->skybox[k].height <= 0 || s->skybox[k].width != s->skybox[0].width
+                    || s->skybox[k].height != s->skybox[0].height)
+                    throw std::invalid_argument("RTB_FLAG_USE_SKYBOX needs six skybox faces of one size");
             for (int k = 0; k < 6; ++k) h->scene.sky[k] = uploadImage(h, s->skybox[k]);
+        }
         // the header's resident copy (out-of-line device helpers read it): only now are all of its pointers final
         h->sceneDev = upload(h, &h->scene, 1);
+        CK(cudaMallocHost(&h->scenePinned, sizeof(rt::Scene)));
         return RTB_OK;
     });
     if (rc != RTB_OK) { destroyHandle(h); return rc; }
@@ -918,13 +967,12 @@ int rtb_set_camera(RtbHandle* h, const RtbCamera* camera)
 {
     if (!h || !camera) { g_err = "null argument"; return RTB_ERR_ARG; }
     return guarded([&]() {
-        CK(cudaSetDevice(h->device));
         h->scene.camPos = rtpack::v3of(camera->pos);
         for (int i = 0; i < 16; ++i) h->scene.camM[i] = camera->rMatrix[i];
         h->scene.camScale = camera->scale;
         h->scene.camAspect = camera->aspect;
-        CK(cudaStreamSynchronize(h->ownStream));
-        CK(cudaMemcpy(h->sceneDev, &h->scene, sizeof(rt::Scene), cudaMemcpyHostToDevice));
+        *h->scenePinned = h->scene;          // uploaded by the next render call on its own stream (uploadSceneHeader)
+        h->sceneDirty = true;
         h->pendingH2D += sizeof(rt::Scene);
         computePrimaryRect(h);
         return RTB_OK;
@@ -959,6 +1007,7 @@ int rtb_render_ac(RtbHandle* h, float* fb, int32_t* counts, int onDevice, void* 
     return guarded([&]() {
         cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
         beginCall(h);
+        uploadSceneHeader(h, st);
         const int total = h->scene.width * h->scene.height;
         // the walk follows the REFERENCE tree, whose depth bounds the stack
         int depth = 1;
@@ -995,7 +1044,7 @@ int rtb_render_ac(RtbHandle* h, float* fb, int32_t* counts, int onDevice, void* 
 int rtb_strip_rows_owned(int height, int stripRowsN, int rank, int worldSize)
 {
     if (height <= 0 || stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return RTB_ERR_ARG;
-    return (int)stripRows(height, stripRowsN, rank, worldSize).size();
+    return (int)stripRows(height, stripRowsN, rank, worldSize, 0).size();
 }
 
 int rtb_render_strips(RtbHandle* h, int stripRowsN, int rank, int worldSize, float* fb, int fbOnDevice, void* stream,
@@ -1004,7 +1053,7 @@ int rtb_render_strips(RtbHandle* h, int stripRowsN, int rank, int worldSize, flo
     if (!h || !fb) { g_err = "null argument"; return RTB_ERR_ARG; }
     if (stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) { g_err = "bad strip partition"; return RTB_ERR_ARG; }
     return guarded([&]() {
-        const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize);
+        const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize, stripOrigin(h));
         if (nRowsOut) *nRowsOut = (int)rows.size();
         return renderRows(h, rows, fb, nullptr, fbOnDevice, stream, stats);
     });
@@ -1015,7 +1064,7 @@ int rtb_render_strips_to_frame(RtbHandle* h, int stripRowsN, int rank, int world
     if (!h || !frame) { g_err = "null argument"; return RTB_ERR_ARG; }
     if (stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) { g_err = "bad strip partition"; return RTB_ERR_ARG; }
     return guarded([&]() {
-        const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize);
+        const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize, stripOrigin(h));
         return renderRows(h, rows, frame, nullptr, 1, stream, stats, OUT_SCATTER);
     });
 }
@@ -1077,6 +1126,16 @@ int rtb_cast(RtbHandle* h, const float* rays, int nRays, float* rgb)
         CK(cudaStreamSynchronize(st));
         return RTB_OK;
     });
+}
+
+int rtb_strip_origin(const RtbHandle* h) { return h ? stripOrigin(h) : RTB_ERR_ARG; }
+
+int rtb_strip_rows(int height, int stripRowsN, int origin, int rank, int worldSize, int32_t* rowsOut)
+{
+    if (height <= 0 || stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) return RTB_ERR_ARG;
+    const std::vector<int> rows = stripRows(height, stripRowsN, rank, worldSize, origin);
+    if (rowsOut) std::copy(rows.begin(), rows.end(), rowsOut);
+    return (int)rows.size();
 }
 
 int rtb_device_of(const RtbHandle* h) { return h ? h->device : RTB_ERR_ARG; }

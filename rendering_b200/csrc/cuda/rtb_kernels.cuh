@@ -1067,13 +1067,15 @@ __global__ void k_ssaa_resolve(const int* __restrict__ flagged, int flaggedCap, 
 // When the geometry's screen-space bounds cover only part of the frame, primary rays are generated for that part
 // only; every other rendered pixel is what castRay returns for a miss without a skybox: the background colour
 // (scene.cpp:383,945).  The last row and column stay black (never rendered, scene.cpp:369-372).
-__global__ void k_fill_background(float* __restrict__ fb, int width, int height, V3 bg)
+// Only the listed rows are written (a rank of a multi-GPU frame touches its strips and their halo, not the frame).
+__global__ void k_fill_background(float* __restrict__ fb, int width, int height, const int* __restrict__ rows, int nRows, V3 bg)
 {
-    const long long total = (long long)width * height;
+    const long long total = (long long)width * nRows;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / width), x = (int)(i - (long long)y * width);
+        const int r = (int)(i / width), x = (int)(i - (long long)r * width);
+        const int y = rows[r];
         const bool rendered = x < width - 1 && y < height - 1;
-        storeSlot(fb, (int)i, rendered ? bg : mk(0.0f, 0.0f, 0.0f));
+        storeSlot(fb, y * width + x, rendered ? bg : mk(0.0f, 0.0f, 0.0f));
     }
 }
 

@@ -169,6 +169,18 @@ inline void primaryRect(const rt::Scene& sc, const std::vector<std::array<float,
     const int wm1 = sc.width - 1, hm1 = sc.height - 1;
     r[0] = 0; r[1] = wm1; r[2] = 0; r[3] = hm1;
     if (unbounded || (sc.flags & rt::FLAG_SKYBOX)) return;
+    // The projection below inverts rMatrix by transposing its 3x3 block, which is only right for what Camera::getRay builds
+    // (a pure rotation, scene.cpp:24-48).  rtb_set_camera accepts any matrix through the C ABI: anything else — scale, shear,
+    // a translation row or a w column (mulRowVecMatrix applies both) — renders the whole frame, like the handles that never cull.
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            double d = 0;
+            for (int k = 0; k < 3; ++k) d += (double)sc.camM[i * 4 + k] * sc.camM[j * 4 + k];
+            if (!(std::fabs(d - (i == j ? 1.0 : 0.0)) <= 1e-4)) return;
+        }
+        if (sc.camM[i * 4 + 3] != 0.0f || sc.camM[3 * 4 + i] != 0.0f) return;
+    }
+    if (sc.camM[15] != 1.0f) return;
     double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
     for (const auto& b : bounds) {
         for (int c = 0; c < 8; ++c) {

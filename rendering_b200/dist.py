@@ -16,17 +16,18 @@ import torch.distributed as dist
 DEFAULT_STRIP_ROWS = 16
 
 
-def owned_rows(height: int, strip_rows: int, rank: int, world: int) -> np.ndarray:
-    """Rows of the image rendered by `rank` (ascending).  Mirrors rtb_render_strips (include/rtb.h)."""
+def owned_rows(height: int, strip_rows: int, rank: int, world: int, origin: int = 0) -> np.ndarray:
+    """Rows of the image rendered by `rank` (ascending).  Mirrors rtb_strip_rows (include/rtb.h): strips are counted from
+    row `origin` (Renderer.strip_origin(): the first row that can contain geometry), floor division for the rows above it."""
     y = np.arange(height)
-    return y[(y // strip_rows) % world == rank]
+    return y[np.floor_divide(y - origin, strip_rows) % world == rank]
 
 
-def max_rows(height: int, strip_rows: int, world: int) -> int:
-    return max(len(owned_rows(height, strip_rows, r, world)) for r in range(world))
+def max_rows(height: int, strip_rows: int, world: int, origin: int = 0) -> int:
+    return max(len(owned_rows(height, strip_rows, r, world, origin)) for r in range(world))
 
 
-def gather_frame(local: torch.Tensor, height: int, strip_rows: int, rank: int, world: int, group=None, dst: int = 0):
+def gather_frame(local: torch.Tensor, height: int, strip_rows: int, rank: int, world: int, group=None, dst: int = 0, origin: int = 0):
     """local: [max_rows, width, 3] float32 (first len(owned_rows) rows valid).  Returns the full
     [height, width, 3] frame on `dst`, None elsewhere.  One collective."""
     width = local.shape[1]
@@ -38,7 +39,7 @@ def gather_frame(local: torch.Tensor, height: int, strip_rows: int, rank: int, w
         return None
     frame = torch.empty((height, width, 3), dtype=local.dtype, device=local.device)
     for r in range(world):
-        rows = torch.as_tensor(owned_rows(height, strip_rows, r, world), device=local.device, dtype=torch.long)
+        rows = torch.as_tensor(owned_rows(height, strip_rows, r, world, origin), device=local.device, dtype=torch.long)
         frame.index_copy_(0, rows, bufs[r][: len(rows)])
     return frame
 
@@ -50,22 +51,28 @@ class FrameExchange:
     (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every rank over NVLink), every rank's
     output kernel stores its rows straight into it at their image position (rtb_render_strips_to_frame with the
     peer pointer), and one device-side barrier on the render stream closes the frame: the transfer is the output
-    kernel's own stores, there is no separate collective and no un-permute.
+    kernel's own stores, there is no separate collective and no un-permute.  Two frame buffers alternate so that
+    a rank running ahead never overwrites rows rank 0 is still reading (see render()).
     Fallback ("nccl"): compact per-rank buffers, one torch.distributed.gather over NCCL, rows put back in image
     order with preallocated index tensors (gather_frame above, without its per-call allocations).
     """
 
-    def __init__(self, height: int, width: int, strip_rows: int, rank: int, world: int, device, transport: str = "auto"):
+    def __init__(self, height: int, width: int, strip_rows: int, rank: int, world: int, device, transport: str = "auto", origin: int = 0):
         self.h, self.w, self.strip, self.rank, self.world = height, width, strip_rows, rank, world
+        self.origin = origin    # Renderer.strip_origin() of the scene / camera the exchange is used with (nccl transport needs it)
         self.device = torch.device(device)
         self.transport = "nccl"
         self.frame = None
         if transport in ("auto", "p2p") and world > 1 and self.device.type == "cuda":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                self.frame = symm_mem.empty((height, width, 3), dtype=torch.float32, device=self.device)
-                self.hdl = symm_mem.rendezvous(self.frame, dist.group.WORLD)
+                # two frames, used alternately: see render()
+                self.frames = symm_mem.empty((2, height, width, 3), dtype=torch.float32, device=self.device)
+                self.hdl = symm_mem.rendezvous(self.frames, dist.group.WORLD)
                 self.root_ptr = int(self.hdl.buffer_ptrs[0])
+                self.frame_bytes = height * width * 3 * 4
+                self.parity = 0
+                self.frame = self.frames[0]
                 self.transport = "p2p"
             except Exception as e:   # no VMM / fabric handle support on this box: use the collective
                 if transport == "p2p":
@@ -79,10 +86,10 @@ class FrameExchange:
             if int(flag.item()) == 0:
                 self.transport = "nccl"
         if self.transport == "nccl":
-            self.local = torch.empty((max_rows(height, strip_rows, world), width, 3), dtype=torch.float32, device=self.device)
+            self.local = torch.empty((max_rows(height, strip_rows, world, origin), width, 3), dtype=torch.float32, device=self.device)
             if rank == 0:
                 self.bufs = [torch.empty_like(self.local) for _ in range(world)]
-                self.rows = [torch.as_tensor(owned_rows(height, strip_rows, r, world), device=self.device, dtype=torch.long) for r in range(world)]
+                self.rows = [torch.as_tensor(owned_rows(height, strip_rows, r, world, origin), device=self.device, dtype=torch.long) for r in range(world)]
                 if self.frame is None:
                     self.frame = torch.empty((height, width, 3), dtype=torch.float32, device=self.device)
 
@@ -93,9 +100,17 @@ class FrameExchange:
         on = (lambda: torch.cuda.stream(stream)) if self.device.type == "cuda" else contextlib.nullcontext
         raw = stream.cuda_stream if self.device.type == "cuda" else None
         if self.transport == "p2p":
-            st = renderer.render_strips_to_frame(self.root_ptr, self.strip, self.rank, self.world, stream=raw)
+            # Frames alternate between two symmetric buffers and ONE device-side barrier on the render stream closes each
+            # frame.  Write-after-read safety without a second barrier: a rank stores frame N+2 into the buffer of frame N
+            # only after it passed barrier N+1, which rank 0's stream reaches after everything it enqueued before — in
+            # particular whatever consumes frame N (conversion, copy, a user kernel on this stream).  A consumer on another
+            # stream must order itself before rank 0's next render() call.
+            k = self.parity
+            self.parity ^= 1
+            st = renderer.render_strips_to_frame(self.root_ptr + k * self.frame_bytes, self.strip, self.rank, self.world, stream=raw)
             with on():
                 self.hdl.barrier(channel=0)
+            self.frame = self.frames[k]
             return st, (self.frame if self.rank == 0 else None)
         st = renderer.render_strips_device(self.local.data_ptr(), self.strip, self.rank, self.world, stream=raw)
         with on():

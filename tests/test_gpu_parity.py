@@ -119,7 +119,7 @@ def test_cfg5_4k_frame_vs_oracle_and_partition_properties():
     frame = np.zeros_like(fb)
     for rank in range(8):
         part, _ = r.render_strips(8, rank, 8)
-        frame[rdist.owned_rows(sc.height, 8, rank, 8)] = part
+        frame[r.strip_rows(8, rank, 8)] = part
     assert np.array_equal(frame.view(np.uint32), fb.view(np.uint32))
     again, _ = r.render()
     assert np.array_equal(again.view(np.uint32), fb.view(np.uint32))
@@ -278,9 +278,9 @@ def test_row_ranges_and_strips_reassemble_to_the_full_frame():
     for strip, world in [(8, 2), (5, 3), (1, 4), (100, 2)]:
         frame = np.zeros_like(full)
         for rank in range(world):
-            rows = rdist.owned_rows(sc.height, strip, rank, world)
+            rows = rdist.owned_rows(sc.height, strip, rank, world, r.strip_origin())
             part, st = r.render_strips(strip, rank, world)
-            assert len(part) == len(rows) == r.rows_owned(strip, rank, world)
+            assert len(part) == len(rows) == r.rows_owned(strip, rank, world) and np.array_equal(rows, r.strip_rows(strip, rank, world))
             frame[rows] = part
         assert np.array_equal(frame.view(np.uint32), full.view(np.uint32)), (strip, world)
 
@@ -406,6 +406,53 @@ def test_camera_sweep_on_a_resident_scene():
     r.set_camera()
     again, _ = r.render()
     assert np.array_equal(again.view(np.uint32), base.view(np.uint32))
+
+
+def test_camera_matrix_that_is_not_a_rotation_disables_primary_culling():
+    # rtb_set_camera takes any RtbCamera through the C ABI; the screen-space bounds primary rays are limited to assume a pure
+    # rotation, so a scaled / sheared / translated matrix must render the whole frame, exactly like the handles that never cull
+    from rendering_b200 import _ffi
+    text = ("[options]\nwidth=96\nheight=64\nbackground_color=0.2,0.3,0.4\n[light]\ntype=point\nposition=0,2,0\n"
+            "[object]\ntype=sphere\npos=0.3,0,-4\nradius=0.8\ncolor=0.9,0.5,0.2\n[end]\n")
+    sc = rb.Scene(text=text)
+    fast, exact = rb.Renderer(sc), rb.Renderer(sc, exact_walk=True)
+    base = sc.desc.camera
+    for edit in ("scale", "shear", "translate", "w"):
+        cam = _ffi.RtbCamera.from_buffer_copy(base)
+        m = list(cam.rMatrix)
+        if edit == "scale":
+            m[0] *= 1.7
+        elif edit == "shear":
+            m[1] += 0.4
+        elif edit == "translate":
+            m[12] = 0.25
+        else:
+            m[3] = 0.1
+        for i in range(16):
+            cam.rMatrix[i] = m[i]
+        fast.set_camera_raw(cam)
+        exact.set_camera_raw(cam)
+        a, sa = fast.render()
+        b, _ = exact.render()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), edit
+        assert sa["backgroundPixels"] == 0, edit
+    fast.set_camera_raw(base)
+    a, sa = fast.render()
+    assert sa["backgroundPixels"] > 0          # the loader's own camera: culling is back
+
+
+def test_skybox_flag_needs_six_equal_faces():
+    if not HAVE_ASSETS:
+        pytest.skip("scenes/input assets not present")
+    sc = load("cfg3_reflective_refractive_1080", 64, 48)
+    d = sc.desc
+    keep = d.skybox[2].width
+    d.skybox[2].width = keep // 2            # one face of another size: the reference would index it out of bounds
+    with pytest.raises(rb.RtbError) as e:
+        rb.Renderer(sc)
+    assert e.value.code == -1 and "skybox" in str(e.value)
+    d.skybox[2].width = keep
+    rb.Renderer(sc).close()
 
 
 def test_strips_written_in_place_assemble_the_frame():

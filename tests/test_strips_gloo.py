@@ -16,14 +16,25 @@ from rendering_b200 import dist as rdist
 def test_partition_matches_c_abi_and_covers_every_row_once():
     lib = C.CDLL(_ffi.CUDA_LIB_PATH)
     lib.rtb_strip_rows_owned.restype = C.c_int
+    lib.rtb_strip_rows.restype = C.c_int
+    lib.rtb_strip_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     for height, strip, world in [(1080, 8, 8), (1080, 32, 4), (256, 8, 3), (7, 8, 2), (92, 5, 8)]:
-        seen = np.zeros(height, int)
-        for r in range(world):
-            rows = rdist.owned_rows(height, strip, r, world)
-            assert len(rows) == lib.rtb_strip_rows_owned(height, strip, r, world)
-            seen[rows] += 1
-        assert (seen == 1).all()
+        # strips counted from row `origin` (the first row that can hold geometry): any origin still covers every row once
+        for origin in (0, 1, 7, height // 3, height - 1):
+            seen = np.zeros(height, int)
+            for r in range(world):
+                rows = rdist.owned_rows(height, strip, r, world, origin)
+                out = np.empty(height, np.int32)
+                n = lib.rtb_strip_rows(height, strip, origin, r, world, out.ctypes.data)
+                assert n == len(rows) and np.array_equal(out[:n], rows)
+                if origin == 0:
+                    assert n == lib.rtb_strip_rows_owned(height, strip, r, world)
+                seen[rows] += 1
+            assert (seen == 1).all()
+            # the strip that starts at the origin belongs to rank 0
+            assert origin in rdist.owned_rows(height, strip, 0, world, origin)
     assert lib.rtb_strip_rows_owned(100, 0, 0, 2) < 0     # bad arguments are refused
+    assert lib.rtb_strip_rows(100, 0, 0, 0, 2, None) < 0
 
 
 def _worker(rank, world, port, height, width, strip, out_dir):
