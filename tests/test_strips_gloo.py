@@ -32,7 +32,7 @@ def test_partition_matches_c_abi_and_covers_every_row_once():
                 seen[rows] += 1
             assert (seen == 1).all()
             # the strip that starts at the origin belongs to rank 0
-            assert origin in rdist.owned_rows(height, strip, 0, world, origin)
+            assert origin >= height or origin in rdist.owned_rows(height, strip, 0, world, origin)
     assert lib.rtb_strip_rows_owned(100, 0, 0, 2) < 0     # bad arguments are refused
     assert lib.rtb_strip_rows(100, 0, 0, 0, 2, None) < 0
 
