@@ -16,8 +16,10 @@
 
 #if defined(__CUDACC__)
 #define RT_HD __host__ __device__ __forceinline__
+#define RT_HD_COLD __host__ __device__ __noinline__     // once-per-ray routines with long bodies: one copy, called (see normalize)
 #else
 #define RT_HD inline
+#define RT_HD_COLD inline
 // plain-C++ stand-ins for the CUDA vector types (tests/shim compiles this header with g++)
 struct float4 { float x, y, z, w; };
 struct int2 { int x, y; };
@@ -42,13 +44,38 @@ RT_HD float maxf_(float a, float b) { return (a < b) ? b : a; }
 RT_HD float minf_(float a, float b) { return (b < a) ? b : a; }
 RT_HD float clampf_(float lo, float hi, float v) { return maxf_(lo, minf_(hi, v)); }   // include/util.h:26-29
 
-// Vec3::length / normalize (include/geometry.h:99-112): double sqrt, double reciprocal
-RT_HD float length(V3 v) { return (float)sqrt((double)dot(v, v)); }
+// Vec3::length / normalize (include/geometry.h:99-112): double sqrt, double reciprocal.
+// On the device the double-precision square root / division sequences (~100 instructions each) are kept OUT OF LINE:
+// they run a few times per ray, and inlining them at every call site made the fused kernels' code (120 KB) thrash the
+// instruction cache (ncu: no-instruction stalls, profiles/r2_experiments).
+#if defined(__CUDA_ARCH__) && !defined(RTB_INLINE_FP64)
+__device__ __noinline__ float rt_sqrtViaDouble(float l2) { return (float)sqrt((double)l2); }
+__device__ __noinline__ float rt_rsqrtViaDouble(float l2) { return (float)(1.0 / sqrt((double)l2)); }
+// PointLight::illuminate / area lights: min(1, intensity / (4 pi len2 / 1000)) evaluated in double (lights.cpp:34)
+__device__ __noinline__ float rt_attenuation(float intensity, float len2)
+{
+    const double att = (double)intensity / (4 * 3.14159265358979323846 * (double)len2 / 1000);
+    const float a = (float)att;
+    return (a < 1.0f) ? a : 1.0f;      // std::min(1.0f, a): a wins only on strict compare
+}
+#define RT_NOINLINE_DEVICE __device__ __noinline__
+#else
+RT_HD float rt_sqrtViaDouble(float l2) { return (float)sqrt((double)l2); }
+RT_HD float rt_rsqrtViaDouble(float l2) { return (float)(1.0 / sqrt((double)l2)); }
+RT_HD float rt_attenuation(float intensity, float len2)
+{
+    const double att = (double)intensity / (4 * 3.14159265358979323846 * (double)len2 / 1000);
+    const float a = (float)att;
+    return (a < 1.0f) ? a : 1.0f;
+}
+#define RT_NOINLINE_DEVICE inline
+#endif
+RT_HD float length(V3 v) { return rt_sqrtViaDouble(dot(v, v)); }
 RT_HD V3 normalize(V3 v)
 {
     const float l2 = dot(v, v);
     if (l2 > 0) {
-        const float k = (float)(1.0 / sqrt((double)l2));
+        const float k = rt_rsqrtViaDouble(l2);
         v.x *= k; v.y *= k; v.z *= k;
     }
     return v;
@@ -404,8 +431,7 @@ RT_HD void illuminate(const Light& li, V3 P, V3& L, V3& I, float& dist)
         dist = FLT_MAX;
     } else {
         L = P - li.v;
-        const double att = (double)li.intensity / (4 * 3.14159265358979323846 * (double)dot(L, L) / 1000);
-        I = li.color * minf_(1.0f, (float)att);
+        I = li.color * rt_attenuation(li.intensity, dot(L, L));
         L = normalize(L);
         dist = length(P - li.v);
     }
@@ -414,8 +440,7 @@ RT_HD void illuminate(const Light& li, V3 P, V3& L, V3& I, float& dist)
 RT_HD V3 areaIntensity(const Light& li, V3 P)
 {
     const V3 d = P - li.v;
-    const double att = (double)li.intensity / (4 * 3.14159265358979323846 * (double)dot(d, d) / 1000);
-    return li.color * minf_(1.0f, (float)att);
+    return li.color * rt_attenuation(li.intensity, dot(d, d));
 }
 
 RT_HD V3 reflect(V3 dir, V3 n) { return dir - n * (2 * dot(dir, n)); }   // scene.cpp:672-675
@@ -534,7 +559,7 @@ RT_HD int powfCheckInt(uint32_t iy)
     return 2;
 }
 
-RT_HD float powfGlibc(float x, float y)
+RT_HD_COLD float powfGlibc(float x, float y)
 {
 #if defined(__CUDA_ARCH__)
     const unsigned long long* logTab = kPowfLog2TabDev;

@@ -97,6 +97,7 @@ struct RtbHandle {
     int primRect[4] = { 0, 0, 0, 0 };  // pixel columns [x0,x1) and rows [y0,y1) primary rays are generated for
     uint64_t pendingH2D = 0;           // bytes uploaded by rtb_set_camera since the last render call (reported in its stats)
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
+    bool spawns = false;               // some object is Reflective / Transparent (their shade branches exist even when maxRayDepth == 0)
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
     int walkBlocksPerSm[4] = { 1, 1, 1, 1 };   // resident CTAs per SM of k_walk<false, GEN 0..2> / k_walk<true> with that stack
 
@@ -371,7 +372,7 @@ size_t tileSmemBytes(const RtbHandle* h)
 void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk::GenArgs& gen, long long total, rtk::RayQueue userQ = rtk::RayQueue{},
     int nUser = 0)
 {
-    const bool deep = h->levels > 1;
+    const bool deep = h->spawns;
     const bool stats = h->createFlags & RTB_CREATE_WALK_STATS;
     const bool staged = h->tileStaged && !stats && h->stagedNodes > 0;
     const size_t smem = staged ? rtk::tileSmemStagedOffset(kStagedGroups, h->stackEntries) + (size_t)h->stagedNodes * 64 + (size_t)h->stagedTris * 48
@@ -648,8 +649,12 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
         if (!initRows.empty()) {
             // culled: background colour where a primary ray would miss by construction; else Vec3f() zero-init (scene.cpp:599)
             KernelSpan ks(h, st, RTB_K_RAYGEN);
+            // pixels that get a generated primary ray are written by pass 1 itself (hit or miss): skip them.  A listed row inside
+            // the rectangle's row range is always a pass-1 row when SSAA is on (initRows = pass-1 rows + the last image row).
+            const bool skip = ssaa && !genRows.empty() && genCols > 0;
+            const int skipY0 = culled ? rect[2] : 0, skipY1 = culled ? rect[3] : ht - 1;
             rtk::k_fill_background<<<gridFor(h, (long long)initRows.size() * w), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, ht, h->rowsC.as<int>(),
-                (int)initRows.size(), culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f));
+                (int)initRows.size(), culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f), skip ? genX0 : 0, skip ? genX0 + genCols : 0, skipY0, skip ? skipY1 : skipY0);
             ks.done();
         }
         CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
@@ -918,6 +923,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         for (int i = 0; i < s->nObjects; ++i)
             spawns |= s->objects[i].material == RTB_MAT_REFLECTIVE || s->objects[i].material == RTB_MAT_TRANSPARENT;
         h->levels = spawns ? std::max(0, s->maxRayDepth) + 1 : 1;
+        h->spawns = spawns;
         if (h->levels > rtk::kMaxTileLevels) h->tilePipeline = false;   // the per-tile level table is fixed-size; deeper trees run frame-wide
         h->ctrBytes = sizeof(rtk::FrameCtr) + 2 * (size_t)(h->levels + 1) * sizeof(rtk::LevelCtr);
         h->ctrBuf.reserve(h->ctrBytes, h->ownStream, false);

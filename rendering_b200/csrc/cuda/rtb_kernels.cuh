@@ -276,6 +276,8 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int cap,
 // ------------------------------------------------------------------------------------------------
 // Threads `first`, `first + step`, ... of a group of `step` threads (a multiple of 32) share the work; `nSurf` is the
 // group's compaction counter (global memory for the frame-wide pipeline, shared memory for a tile).
+// MISSES = false compiles the miss branch (skybox lookup) out: rays generated inside the walk resolve their own misses.
+template <bool MISSES = true>
 __device__ __forceinline__ void surfaceStage(const Scene& sc, RayQueue q, HitQueue hits, SurfQueue surf, const Slots& slots, int n, int first, int step,
     int* nSurf, int handleMisses)
 {
@@ -286,10 +288,10 @@ __device__ __forceinline__ void surfaceStage(const Scene& sc, RayQueue q, HitQue
         int obj = -1;
         // rays generated inside the walk resolve their own misses (handleMisses == 0): only obj is valid for those
         if (i < n) obj = hits.obj[i];
-        if (i < n && (obj >= 0 || (handleMisses && q.dest[i] != -1))) {
+        if (i < n && (obj >= 0 || (MISSES && handleMisses && q.dest[i] != -1))) {
             const float4 d4 = q.d[i];
             const V3 d = mk(d4.x, d4.y, d4.z);
-            if (obj < 0) {
+            if (MISSES && obj < 0) {
                 storeSlot(slots, q.dest[i], skybox(sc, d));
             } else {
                 const float4 o4 = q.o[i], h = hits.tuv[i];
@@ -448,11 +450,7 @@ struct GenArgs {
 // Kept out of line so their FP64 normalisation / cube-map code does not raise the register count of the
 // traversal loop (they run once per ray, the loop runs ~100 times).
 __device__ __noinline__ V3 genCameraRay(const Scene* sc, float px, float py) { return cameraDir(*sc, px, py); }
-__device__ __noinline__ void storeMissColour(const Scene* sc, float* p, V3 d)
-{
-    const V3 c = skybox(*sc, d);
-    p[0] = c.x; p[1] = c.y; p[2] = c.z;
-}
+__device__ __noinline__ V3 missColour(const Scene* sc, V3 d) { return skybox(*sc, d); }
 
 #ifndef RTB_WALK_MIN_BLOCKS
 #define RTB_WALK_MIN_BLOCKS 9   // 56 registers, 9 CTAs per SM: measured 1-2 % faster than 64 / 78 registers at 8 / 6 CTAs
@@ -477,16 +475,20 @@ __device__ __forceinline__ float4 ldsF4(unsigned addr)
 // per-thread tallies of a walk, flushed by the caller (once per kernel)
 struct WalkAcc {
     unsigned nSkipped = 0;                                 // shadow rays elided
-    unsigned long long nNodes = 0, nTris = 0, nElig = 0;   // STATS only
+    unsigned long long nNodes[2] = { 0, 0 }, nTris[2] = { 0, 0 }, nElig[2] = { 0, 0 };   // STATS only; [0] closest-hit rays, [1] shadow rays
 };
 
 // The traversal loop.  All 32 lanes of a warp must call it together; warps are otherwise independent and pull rays
 // [0, total) from `cursor` (global memory for a frame-wide launch, shared memory for one tile's stage).  Indices are
 // relative to the queues handed in; generated rays map index `my` to pixel / sample number genOffset + my.
 // STRIDE = distance in ints between a thread's consecutive stack entries (the thread count of the stack's owner).
-template <bool ANY, int GEN, bool STATS, int STRIDE, typename CursorT, bool STAGED = false>
-__device__ __forceinline__ void walkRays(const Scene& sc, RayQueue q, HitQueue hits, SurfQueue surf, unsigned char* vis, int nSurfRaw,
-    const GenArgs& gen, long long genOffset, const Slots& slots, CursorT* cursor, long long total, int* stack, WalkAcc& acc,
+// ANY and GEN are RUN-TIME, warp-uniform arguments on purpose: a fused kernel walks closest-hit rays, shadow rays and
+// (deep scenes) queued secondary rays, and calls this function from ONE site in a small loop, so one copy of the loop
+// (~25 KB of SASS) serves all of them.  As template parameters every kind had its own inlined copy and the kernels grew
+// past the instruction cache (ncu: no-instruction stalls 1.1 per issue in the 120 KB k_tile; profiles/r2_experiments).
+template <bool STATS, int STRIDE, typename CursorT, bool STAGED = false>
+__device__ __forceinline__ void walkRays(const bool ANY, const int GEN, const Scene& sc, RayQueue q, HitQueue hits, SurfQueue surf, unsigned char* vis,
+    int nSurfRaw, const GenArgs& gen, long long genOffset, const Slots& slots, CursorT* cursor, long long total, int* stack, WalkAcc& acc,
     const StagedBvh& sb = StagedBvh{})
 {
     const unsigned FULL = 0xffffffffu;
@@ -609,7 +611,7 @@ __device__ __forceinline__ void walkRays(const Scene& sc, RayQueue q, HitQueue h
                         } else {
                             hits.obj[out] = objN;
                             if (objN < 0) {
-                                storeMissColour(gen.scene, slotAddr(slots, dest), r.d);    // castRay's miss branch (scene.cpp:945)
+                                storeSlot(slots, dest, missColour(gen.scene, r.d));        // castRay's miss branch (scene.cpp:945)
                             } else {
                                 hits.tuv[out] = make_float4(tNear, uN, vN, __int_as_float(triN));
                                 q.o[out] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
@@ -660,7 +662,7 @@ __device__ __forceinline__ void walkRays(const Scene& sc, RayQueue q, HitQueue h
                             const float4* nd = me->bvhNodes + (size_t)cur * 4;
                             a = __ldg(nd); b = __ldg(nd + 1); c = __ldg(nd + 2); d = __ldg(nd + 3);
                         }
-                        if (STATS) acc.nNodes++;
+                        if (STATS) acc.nNodes[ANY]++;
                         const float tFar = ANY ? tNear : tM;
                         bool h0, h1;
                         const float e0 = slabEntry(r, a.x, a.y, a.z, a.w, b.x, b.y, tFar, h0);
@@ -692,14 +694,14 @@ __device__ __forceinline__ void walkRays(const Scene& sc, RayQueue q, HitQueue h
                         if (trisStaged) { p0 = ldsF4(ta); p1 = ldsF4(ta + 16); p2 = ldsF4(ta + 32); }
                         else { p0 = __ldg(tp); p1 = __ldg(tp + 1); p2 = __ldg(tp + 2); }
                         float t, u, v;
-                        if (STATS) acc.nTris++;
+                        if (STATS) acc.nTris[ANY]++;
                         if (!hitTriangle(r, mk(p0.x, p0.y, p0.z), mk(p1.x, p1.y, p1.z), mk(p2.x, p2.y, p2.z), cull, t, u, v)) continue;
                         const int tri = __float_as_int(p0.w);
                         if (ANY) {
-                            if (STATS && t < tNear) acc.nElig++;
+                            if (STATS && t < tNear) acc.nElig[ANY]++;
                             if (t < tNear && eligibleSlot(sc, *me, r, tri) >= 0) { blocked = true; break; }
                         } else if (t < tM || (found && t == tM)) {
-                            if (STATS) acc.nElig++;
+                            if (STATS) acc.nElig[ANY]++;
                             const int slot = eligibleSlot(sc, *me, r, tri);
                             if (slot >= 0 && (t < tM || slot < slotBest)) { tM = t; uM = u; vM = v; triM = tri; slotBest = slot; found = true; }
                         }
@@ -746,12 +748,12 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
     else total = min(lv->nRays, cap);
     if (!ANY && GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
     WalkAcc acc;
-    walkRays<ANY, GEN, STATS, kBlock>(sc, q, hits, surf, vis, nSurfRaw, gen, 0LL, Slots{ gen.slots, nullptr }, cursor, total, stack, acc);
+    walkRays<STATS, kBlock>(ANY, GEN, sc, q, hits, surf, vis, nSurfRaw, gen, 0LL, Slots{ gen.slots, nullptr }, cursor, total, stack, acc);
     if (ANY) flushWalkAcc(ctr, acc, STATS);
     if (STATS) {
-        atomicAdd(&ctr->walkNodes[ANY ? 1 : 0], acc.nNodes);
-        atomicAdd(&ctr->walkTris[ANY ? 1 : 0], acc.nTris);
-        atomicAdd(&ctr->walkEligibility[ANY ? 1 : 0], acc.nElig);
+        atomicAdd(&ctr->walkNodes[ANY ? 1 : 0], acc.nNodes[ANY]);
+        atomicAdd(&ctr->walkTris[ANY ? 1 : 0], acc.nTris[ANY]);
+        atomicAdd(&ctr->walkEligibility[ANY ? 1 : 0], acc.nElig[ANY]);
     }
 }
 
@@ -774,6 +776,8 @@ struct ShadeOut {
     int* overflow;
 };
 
+// DEEP = false compiles the Reflective / Transparent branches and the child bookkeeping out (no such object in the scene).
+template <bool DEEP = true>
 __device__ __forceinline__ void shadeStage(const Scene& sc, RayQueue q, SurfQueue surf, const unsigned char* vis, int depth, int n, int first, int step,
     const Slots& slots, const ShadeOut& o)
 {
@@ -829,7 +833,7 @@ __device__ __forceinline__ void shadeStage(const Scene& sc, RayQueue q, SurfQueu
 
             if (mat == MAT_DIFFUSE) {
                 storeSlot(slots, dest, color * diff);                                                 // :809
-            } else if (mat == MAT_PHONG) {
+            } else if (mat == MAT_PHONG || !DEEP) {
                 storeSlot(slots, dest, color * ob.ambient + diff * ob.diffuse + spec * p4.w);         // :852
             } else if (mat == MAT_REFLECTIVE) {
                 const V3 ro = P + N * sc.bias;
@@ -867,6 +871,7 @@ __device__ __forceinline__ void shadeStage(const Scene& sc, RayQueue q, SurfQueu
                 }
             }
         }
+        if (!DEEP) continue;
         // bump-allocate: interior record, two colour slots, nChildren queue entries
         const int ii = warpAlloc(o.interiorCount, wantInterior, 1);
         const int cs = o.slotBase + (o.slotCount ? warpAlloc(o.slotCount, wantInterior, 2) : 2 * ii);
@@ -950,85 +955,106 @@ __global__ void k_combine(const Interior* __restrict__ interiors, const LevelCtr
 // SSAA: Sobel mask on the unclamped float frame, then 4 re-traced samples per flagged pixel
 // ------------------------------------------------------------------------------------------------
 // rows[]: image rows owned by this call; only interior pixels get a flag (scene.cpp:554-555).  Pixels are
-// visited in the 8x4 tiles of ray generation (one warp = one tile), so the compacted list keeps
-// neighbouring pixels — and with them the 4 samples of each — next to each other in the SSAA ray queue.
+// visited in the 8x4 tiles of ray generation, so the compacted list keeps neighbouring pixels — and with them the 4
+// samples of each — next to each other in the SSAA ray queue.
+// One warp handles a block of kSobelTiles horizontally adjacent 8x4 tiles per iteration: the block's (8 kSobelTiles + 2) x 6
+// pixel neighbourhood is staged in shared memory with all its coalesced row loads in flight at once, every lane then
+// evaluates one pixel of each tile, and ONE atomicAdd reserves the list entries of the whole block (the kernel was bound by
+// the latency of one small load group and one returning atomic per 32 pixels: 33 us for the 1080p frame).
+constexpr int kSobelTiles = 4;
+constexpr int kSobelRowFloats = (8 * kSobelTiles + 2) * 3;      // 102
 __global__ void __launch_bounds__(kBlock) k_sobel(int width, int height, const float* __restrict__ fb, const int* __restrict__ rows, int nRows,
     int* __restrict__ flagged, int flaggedCap, FrameCtr* ctr)
 {
-    // one warp = one 8x4 pixel tile; its 10x6 pixel neighbourhood (180 floats per channel row) is staged in shared
-    // memory with coalesced row loads when the tile's four rows are consecutive image rows (always, unless a strip
-    // partition cuts through the tile); otherwise every lane reads its 3x3 window directly
-    __shared__ float tileMem[kBlock / 32][6][33];      // rows padded to 33 floats: the 4 pixel rows of a warp hit different banks
-    float (*tile)[33] = tileMem[threadIdx.x >> 5];
-    const int tilesX = (width + 7) / 8;
-    const long long total = (long long)tilesX * ((nRows + 3) / 4) * 32;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        bool flag = false;
-        int pix = 0;
-        const long long tileIdx = i >> 5;
-        const int lane = (int)(i & 31);
-        const int x0 = (int)(tileIdx % tilesX) * 8, r0 = (int)(tileIdx / tilesX) * 4;
-        const int x = x0 + (lane & 7), r = r0 + (lane >> 3);
+    __shared__ float tileMem[kBlock / 32][6][kSobelRowFloats + 1];
+    float (*tile)[kSobelRowFloats + 1] = tileMem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int blocksX = (width + 8 * kSobelTiles - 1) / (8 * kSobelTiles);
+    const long long total = (long long)blocksX * ((nRows + 3) / 4);
+    const long long warpId = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float op[3][3] = { { -1, 0, 1 }, { -2, 0, 2 }, { -1, 0, 1 } };
+    for (long long blk = warpId; blk < total; blk += nWarps) {
+        const int x0 = (int)(blk % blocksX) * 8 * kSobelTiles, r0 = (int)(blk / blocksX) * 4;
+        const int r = r0 + (lane >> 3);
         const int yFirst = rows[r0], rLast = min(r0 + 3, nRows - 1);
+        // the block's rows are consecutive image rows (always, unless a strip partition cuts through it): stage them;
+        // otherwise every lane reads its 3x3 windows directly
         const bool staged = rows[rLast] - yFirst == rLast - r0 && yFirst >= 1 && yFirst + (rLast - r0) < height - 1;
-        const bool inside = x < width && r < nRows;
-        const int y = inside ? rows[r] : 0;
-        const bool interior = inside && y >= 1 && y < height - 1 && x >= 1 && x < width - 1;
-        V3 gx = mk(0.0f, 0.0f, 0.0f), gy = mk(0.0f, 0.0f, 0.0f);
-        const float op[3][3] = { { -1, 0, 1 }, { -2, 0, 2 }, { -1, 0, 1 } };
+        const int y = r < nRows ? rows[r] : 0;
         if (staged) {
-            // rows yFirst-1 .. yFirst+4, columns x0-1 .. x0+8: 30 floats per row, lanes 0..29 load one each
             const int cBase = (x0 - 1) * 3;
             __syncwarp();
 #pragma unroll
             for (int rr = 0; rr < 6; ++rr) {
-                const int yy = yFirst - 1 + rr;
-                const int c = cBase + lane;
-                float v = 0.0f;
-                if (lane < 30 && yy < height && c >= 0 && c < width * 3) v = fb[(size_t)yy * width * 3 + c];
-                tile[rr][lane] = v;
+                const size_t rowOff = (size_t)(yFirst - 1 + rr) * width * 3;
+#pragma unroll
+                for (int k = 0; k < (kSobelRowFloats + 31) / 32; ++k) {
+                    const int j = k * 32 + lane, c = cBase + j;
+                    if (j < kSobelRowFloats) tile[rr][j] = (yFirst - 1 + rr < height && c >= 0 && c < width * 3) ? fb[rowOff + c] : 0.0f;
+                }
             }
             __syncwarp();
+        }
+        unsigned votes[kSobelTiles];
+        int pixOf[kSobelTiles];
+#pragma unroll
+        for (int t = 0; t < kSobelTiles; ++t) {
+            const int x = x0 + t * 8 + (lane & 7);
+            const bool interior = x < width && r < nRows && y >= 1 && y < height - 1 && x >= 1 && x < width - 1;
+            bool flag = false;
             if (interior) {
-                const int ly = y - yFirst, lx = (lane & 7) * 3;   // window rows ly..ly+2, float columns lx..lx+8
+                V3 gx = mk(0.0f, 0.0f, 0.0f), gy = mk(0.0f, 0.0f, 0.0f);
+                if (staged) {
+                    const int ly = y - yFirst, lx = (t * 8 + (lane & 7)) * 3;   // window rows ly..ly+2, float columns lx..lx+8
 #pragma unroll
-                for (int a = 0; a < 3; ++a)
+                    for (int a = 0; a < 3; ++a)
 #pragma unroll
-                    for (int b = 0; b < 3; ++b) {
-                        const V3 c = mk(tile[ly + a][lx + 3 * b], tile[ly + a][lx + 3 * b + 1], tile[ly + a][lx + 3 * b + 2]);
-                        gx = gx + c * op[a][b];
-                        gy = gy + c * op[b][a];
-                    }
-            }
-        } else if (interior) {
+                        for (int b = 0; b < 3; ++b) {
+                            const V3 c = mk(tile[ly + a][lx + 3 * b], tile[ly + a][lx + 3 * b + 1], tile[ly + a][lx + 3 * b + 2]);
+                            gx = gx + c * op[a][b];
+                            gy = gy + c * op[b][a];
+                        }
+                } else {
 #pragma unroll
-            for (int a = 0; a < 3; ++a)
+                    for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const V3 c = loadSlot(fb, (y - 1 + a) * width + x - 1 + b);
-                    gx = gx + c * op[a][b];
-                    gy = gy + c * op[b][a];
+                        for (int b = 0; b < 3; ++b) {
+                            const V3 c = loadSlot(fb, (y - 1 + a) * width + x - 1 + b);
+                            gx = gx + c * op[a][b];
+                            gy = gy + c * op[b][a];
+                        }
                 }
-        }
-        if (interior) {
-            // val = sqrtf(powf(|Gx|,2) + powf(|Gy|,2)) > 0.5f with |G| = (float)sqrt((double)G.G)  (scene.cpp:565-566,
-            // geometry.h:99).  Away from the threshold the float sum of squares decides with a wide margin and the
-            // double-precision square roots are skipped.
-            const float s2 = dot(gx, gx) + dot(gy, gy);
-            if (s2 > 0.2501f) flag = true;
-            else if (s2 < 0.2499f) flag = false;
-            else {
-                // powf(v, 2) is compiled to v * v: GCC expands pow with the exponents -1, 0, 1, 2 inline at every
-                // optimisation level (no libm call in the reference binary's launchSSAA), unlike castRay's powf(x, nSpecular)
-                const float lx = length(gx), ly = length(gy);
-                flag = sqrtf(lx * lx + ly * ly) > 0.5f;
+                // val = sqrtf(powf(|Gx|,2) + powf(|Gy|,2)) > 0.5f with |G| = (float)sqrt((double)G.G)  (scene.cpp:565-566,
+                // geometry.h:99).  Away from the threshold the float sum of squares decides with a wide margin and the
+                // double-precision square roots are skipped.
+                const float s2 = dot(gx, gx) + dot(gy, gy);
+                if (s2 > 0.2501f) flag = true;
+                else if (s2 < 0.2499f) flag = false;
+                else {
+                    // powf(v, 2) is compiled to v * v: GCC expands pow with the exponents -1, 0, 1, 2 inline at every
+                    // optimisation level (no libm call in the reference binary's launchSSAA), unlike castRay's powf(x, nSpecular)
+                    const float lx = length(gx), ly = length(gy);
+                    flag = sqrtf(lx * lx + ly * ly) > 0.5f;
+                }
             }
-            pix = y * width + x;
+            votes[t] = __ballot_sync(0xffffffffu, flag);
+            pixOf[t] = y * width + x;
         }
-        const int f = warpAlloc(&ctr->ssaaPixels, flag, 1);
-        if (flag) {
-            if (f < flaggedCap) flagged[f] = pix;
-            else atomicOr(&ctr->overflow, OVF_FLAGGED);
+        int count = 0;
+#pragma unroll
+        for (int t = 0; t < kSobelTiles; ++t) count += __popc(votes[t]);
+        if (count == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ctr->ssaaPixels, count);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int t = 0; t < kSobelTiles; ++t) {      // tile by tile: the list keeps the 8x4 locality
+            if (votes[t] & (1u << lane)) {
+                const int f = base + __popc(votes[t] & ((1u << lane) - 1));
+                if (f < flaggedCap) flagged[f] = pixOf[t];
+                else atomicOr(&ctr->overflow, OVF_FLAGGED);
+            }
+            base += __popc(votes[t]);
         }
     }
 }
@@ -1067,13 +1093,17 @@ __global__ void k_ssaa_resolve(const int* __restrict__ flagged, int flaggedCap, 
 // When the geometry's screen-space bounds cover only part of the frame, primary rays are generated for that part
 // only; every other rendered pixel is what castRay returns for a miss without a skybox: the background colour
 // (scene.cpp:383,945).  The last row and column stay black (never rendered, scene.cpp:369-372).
-// Only the listed rows are written (a rank of a multi-GPU frame touches its strips and their halo, not the frame).
-__global__ void k_fill_background(float* __restrict__ fb, int width, int height, const int* __restrict__ rows, int nRows, V3 bg)
+// Only the listed rows are written (a rank of a multi-GPU frame touches its strips and their halo, not the frame), and of
+// those only the pixels outside columns [sx0, sx1) x rows [sy0, sy1): every pixel inside is a generated primary ray, whose
+// colour the pass-1 kernel stores whether it hits or misses.
+__global__ void k_fill_background(float* __restrict__ fb, int width, int height, const int* __restrict__ rows, int nRows, V3 bg,
+    int sx0, int sx1, int sy0, int sy1)
 {
     const long long total = (long long)width * nRows;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / width), x = (int)(i - (long long)r * width);
         const int y = rows[r];
+        if (x >= sx0 && x < sx1 && y >= sy0 && y < sy1) continue;
         const bool rendered = x < width - 1 && y < height - 1;
         storeSlot(fb, y * width + x, rendered ? bg : mk(0.0f, 0.0f, 0.0f));
     }

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kTileThreads * NG, NG == 1 ? RTB_TILE_MIN_BLOC
     else total = a.nUser;
     if (GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) a.lv[0].nRays = (int)min(total, 0x7fffffffLL);
 
-    WalkAcc accClosest, accShadow;
+    WalkAcc acc;
 
     for (;;) {
         if (gtid == 0) {
@@ -227,29 +227,36 @@ __global__ void __launch_bounds__(kTileThreads * NG, NG == 1 ? RTB_TILE_MIN_BLOC
             if (GEN == GEN_QUEUE && depth == 0) q = RayQueue{ a.userQ.o + base, a.userQ.d + base, a.userQ.dest + base };
             const RayQueue next = ts.q[(depth + 1) & 1];
             lastLevel = depth;
+            int nSurf = 0;
 
-            // ---- closest hit (Render::trace) ----
-            if (depth == 0) walkRays<false, GEN, STATS, kTileThreads, unsigned, STAGED>(sc, q, ts.hits, ts.surf, ts.vis, 0, a.gen, base, slots, &lc.cursorClosest, (long long)n, stack, accClosest, sb);
-            else if (DEEP) walkRays<false, GEN_QUEUE, STATS, kTileThreads, unsigned, STAGED>(sc, q, ts.hits, ts.surf, ts.vis, 0, a.gen, 0LL, slots, &lc.cursorClosest, (long long)n, stack, accClosest, sb);
-            groupSync<NG>(group);
-            // the other parity's counters are idle now: every thread has read the previous level's nNext before its walk
-            if (gtid == 0) gs.lv[(depth + 1) & 1] = TileLevelCtr{ 0u, 0u, 0, 0 };
-
-            // ---- surface records, hits compacted (castRay :762-775); misses of queued rays -> skybox ----
-            surfaceStage(sc, q, ts.hits, ts.surf, slots, n, gtid, kTileThreads, &lc.nSurf, (depth > 0 || GEN == GEN_QUEUE) ? 1 : 0);
-            groupSync<NG>(group);
-            const int nSurf = lc.nSurf;
-
-            if (!showNormals) {
-                // ---- shadow rays, light-major ----
-                if (S > 0 && nSurf > 0) {
-                    walkRays<true, GEN_QUEUE, STATS, kTileThreads, unsigned, STAGED>(sc, q, ts.hits, ts.surf, ts.vis, nSurf, a.gen, 0LL, slots, &lc.cursorShadow, (long long)nSurf * S, stack, accShadow, sb);
+            // Two walks per level — closest hit (Render::trace), then the shadow rays of its hits, light-major — through ONE
+            // call site (see walkRays: one copy of the traversal loop in the kernel).  The surface stage sits between them.
+#pragma unroll 1
+            for (int phase = 0; phase < 2; ++phase) {
+                const bool any = phase != 0;
+                unsigned* cursor = &lc.cursorClosest;
+                long long count = n;
+                int genKind = (depth == 0) ? GEN : GEN_QUEUE;
+                if (any) {
+                    // the other parity's counters are idle now: every thread has read the previous level's nNext before its walk
+                    if (gtid == 0) gs.lv[(depth + 1) & 1] = TileLevelCtr{ 0u, 0u, 0, 0 };
+                    // ---- surface records, hits compacted (castRay :762-775); misses of queued rays -> skybox ----
+                    surfaceStage<(DEEP || GEN == GEN_QUEUE)>(sc, q, ts.hits, ts.surf, slots, n, gtid, kTileThreads, &lc.nSurf, (depth > 0 || GEN == GEN_QUEUE) ? 1 : 0);
                     groupSync<NG>(group);
+                    nSurf = lc.nSurf;
+                    if (showNormals || S <= 0 || nSurf <= 0) break;
+                    cursor = &lc.cursorShadow;
+                    count = (long long)nSurf * S;
+                    genKind = GEN_QUEUE;
                 }
+                walkRays<STATS, kTileThreads, unsigned, STAGED>(any, genKind, sc, q, ts.hits, ts.surf, ts.vis, nSurf, a.gen, base, slots, cursor, count, stack, acc, sb);
+                groupSync<NG>(group);
+            }
+            if (!showNormals) {
                 // ---- shade; Reflective / Transparent hits leave a record and queue their children ----
                 const ShadeOut so{ next, a.capRays, &lc.nNext, ts.interiors, a.capInterior, &gs.interiors, nullptr, nullptr, R, R + 2 * a.capInterior,
                     true, &a.ctr->overflow };
-                shadeStage(sc, q, ts.surf, ts.vis, depth, nSurf, gtid, kTileThreads, slots, so);
+                shadeStage<DEEP>(sc, q, ts.surf, ts.vis, depth, nSurf, gtid, kTileThreads, slots, so);
                 groupSync<NG>(group);
             }
             if (gtid == 0) {
@@ -284,10 +291,10 @@ __global__ void __launch_bounds__(kTileThreads * NG, NG == 1 ? RTB_TILE_MIN_BLOC
         groupSync<NG>(group);     // everybody is done with this tile's shared state
     }
 
-    flushWalkAcc(a.ctr, accShadow, STATS);
+    flushWalkAcc(a.ctr, acc, STATS);
     if (STATS) {
-        atomicAdd(&a.ctr->walkNodes[0], accClosest.nNodes); atomicAdd(&a.ctr->walkTris[0], accClosest.nTris); atomicAdd(&a.ctr->walkEligibility[0], accClosest.nElig);
-        atomicAdd(&a.ctr->walkNodes[1], accShadow.nNodes); atomicAdd(&a.ctr->walkTris[1], accShadow.nTris); atomicAdd(&a.ctr->walkEligibility[1], accShadow.nElig);
+        atomicAdd(&a.ctr->walkNodes[0], acc.nNodes[0]); atomicAdd(&a.ctr->walkTris[0], acc.nTris[0]); atomicAdd(&a.ctr->walkEligibility[0], acc.nElig[0]);
+        atomicAdd(&a.ctr->walkNodes[1], acc.nNodes[1]); atomicAdd(&a.ctr->walkTris[1], acc.nTris[1]); atomicAdd(&a.ctr->walkEligibility[1], acc.nElig[1]);
     }
 }
 

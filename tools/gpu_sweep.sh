@@ -1,10 +1,9 @@
 #!/bin/bash
-# experiment sweep on the GPU box: tile-pipeline variants (group width / CTAs per SM / tile size) on the main configs
+# experiment sweep on the GPU box: build variants on the main configs (tile pipeline)
 cd "$(dirname "$0")/.."
-CFGS="cfg1_simple_shapes_256 cfg3_reflective_refractive_1080 cfg4_shotgun_1080 cfgD_dragon_1080"
-for lib in default t256b3 t128b8 t128b6; do
-  for R in 0 256 512 1024; do
-    if [ $lib = default ]; then unset RTB_CUDA_LIB; else export RTB_CUDA_LIB=$PWD/build_variants/librtb_cuda_$lib.so; fi
-    RTB_TILE_RAYS=$R RTB_AB_TAG=sweep_${lib}_R$R timeout 300 python tools/gpu_ab.py --tile-only $CFGS 2>&1 | grep SUMMARY
-  done
+CFGS="cfg1_simple_shapes_256 cfg3_reflective_refractive_1080 cfg2_smooth_shading_1024 cfg4_shotgun_1080 cfgD_dragon_1080 cfg5_shotgun_2160"
+unset RTB_CUDA_LIB
+RTB_AB_TAG=sweep_default timeout 300 python tools/gpu_ab.py --tile-only $CFGS 2>&1 | grep -E "SUMMARY|Error|error"
+for lib in "$@"; do
+  RTB_CUDA_LIB=$PWD/build_variants/librtb_cuda_$lib.so RTB_AB_TAG=sweep_$lib timeout 300 python tools/gpu_ab.py --tile-only $CFGS 2>&1 | grep -E "SUMMARY|Error|error"
 done
