@@ -154,6 +154,8 @@ typedef struct RtbStats {
                                      and that the fast path therefore does not trace                      */
     uint64_t backgroundPixels;    /* primary rays (counted in `rays`) that lie outside the screen-space bounds of the
                                      geometry and are resolved by the background pre-fill instead of a traversal     */
+    float    msBuildSearchBvh;    /* time rtb_create spent building the search BVHs (host: wall clock; device: CUDA events);
+                                     a property of the handle, repeated in every call's stats                              */
     uint32_t kernelLaunches;
     uint32_t levels;
     float    msPass1, msSobel, msSSAA, msTotal;   /* CUDA-event times on the render stream         */
@@ -199,6 +201,8 @@ const char* rtb_host_last_error(void);
 #define RTB_CREATE_WALK_STATS (1u << 3)  /* fill RtbStats.walkNodes / walkTris / walkEligibility (slower kernels)    */
 #define RTB_CREATE_WAVEFRONT (1u << 4)   /* frame-wide level pipeline (one launch per stage and recursion level) instead of
                                             the default tile pipeline (whole recursion per tile inside one kernel); same bits */
+#define RTB_CREATE_DEVICE_BVH (1u << 5)  /* build the search BVH on the device (linear BVH: Morton keys, radix sort, Karras tree) instead of
+                                            the host's binned SAH: ~100x faster to build, somewhat slower to traverse, same frames   */
 #define RTB_CREATE_KERNEL_TIMING (1u << 2) /* fill RtbStats.msKernel: CUDA events around every launch (costs ~6 us
                                               of stream time per launch, so it is off by default)               */
 

@@ -20,7 +20,7 @@ RTB_OBJ_SPHERE, RTB_OBJ_PLANE, RTB_OBJ_MESH = 1, 2, 3
 RTB_MAT_DIFFUSE, RTB_MAT_REFLECTIVE, RTB_MAT_TRANSPARENT, RTB_MAT_PHONG = 0, 1, 2, 3
 RTB_LIGHT_DISTANT, RTB_LIGHT_POINT, RTB_LIGHT_AREA = 1, 2, 3
 RTB_FLAG_BACKFACE_CULLING, RTB_FLAG_USE_AC, RTB_FLAG_USE_SKYBOX, RTB_FLAG_SHOW_NORMALS, RTB_FLAG_ENABLE_SSAA = 1, 2, 4, 8, 16
-RTB_CREATE_DEFAULT, RTB_CREATE_COUNTERS, RTB_CREATE_EXACT_WALK, RTB_CREATE_KERNEL_TIMING, RTB_CREATE_WALK_STATS, RTB_CREATE_WAVEFRONT = 0, 1, 2, 4, 8, 16
+RTB_CREATE_DEFAULT, RTB_CREATE_COUNTERS, RTB_CREATE_EXACT_WALK, RTB_CREATE_KERNEL_TIMING, RTB_CREATE_WALK_STATS, RTB_CREATE_WAVEFRONT, RTB_CREATE_DEVICE_BVH = 0, 1, 2, 4, 8, 16, 32
 
 f32, i32, u32, u64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64
 
@@ -65,7 +65,7 @@ class RtbScene(C.Structure):
 
 class RtbStats(C.Structure):
     _fields_ = [("rays", u64), ("primaryRays", u64), ("secondaryRays", u64), ("shadowRays", u64), ("ssaaPixels", u64),
-                ("boxTests", u64), ("triTests", u64), ("boxTestsShadow", u64), ("triTestsShadow", u64), ("h2dBytes", u64), ("d2hBytes", u64), ("shadowRaysSkipped", u64), ("backgroundPixels", u64),
+                ("boxTests", u64), ("triTests", u64), ("boxTestsShadow", u64), ("triTestsShadow", u64), ("h2dBytes", u64), ("d2hBytes", u64), ("shadowRaysSkipped", u64), ("backgroundPixels", u64), ("msBuildSearchBvh", f32),
                 ("kernelLaunches", u32), ("levels", u32),
                 ("msPass1", f32), ("msSobel", f32), ("msSSAA", f32), ("msTotal", f32),
                 ("msKernel", f32 * 10), ("launchesKernel", u32 * 10),

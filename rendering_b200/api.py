@@ -104,13 +104,13 @@ class Renderer:
     """Device-side renderer handle (librtb_cuda.so).  Raises if the CUDA library or a GPU is missing."""
 
     def __init__(self, scene: Scene, device: int = 0, counters: bool = False, exact_walk: bool = False, kernel_timing: bool = False,
-                 walk_stats: bool = False, wavefront: bool = False):
+                 walk_stats: bool = False, wavefront: bool = False, device_bvh: bool = False):
         self._lib = _ffi.cuda_lib()
         self.scene = scene
         self.width, self.height = scene.width, scene.height
         flags = ((_ffi.RTB_CREATE_COUNTERS if counters else 0) | (_ffi.RTB_CREATE_EXACT_WALK if exact_walk else 0)
                  | (_ffi.RTB_CREATE_KERNEL_TIMING if kernel_timing else 0) | (_ffi.RTB_CREATE_WALK_STATS if walk_stats else 0)
-                 | (_ffi.RTB_CREATE_WAVEFRONT if wavefront else 0))
+                 | (_ffi.RTB_CREATE_WAVEFRONT if wavefront else 0) | (_ffi.RTB_CREATE_DEVICE_BVH if device_bvh else 0))
         self._h = C.c_void_p()
         rc = self._lib.rtb_create(scene.view, device, flags, C.byref(self._h))
         if rc != _ffi.RTB_OK:

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cfloat>
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -22,6 +23,7 @@
 #include "rtb_kernels.cuh"
 #include "rtb_tile.cuh"
 #include "scene_pack.h"
+#include "lbvh_build.cuh"
 
 namespace {
 
@@ -96,6 +98,7 @@ struct RtbHandle {
     bool unbounded = false;
     int primRect[4] = { 0, 0, 0, 0 };  // pixel columns [x0,x1) and rows [y0,y1) primary rays are generated for
     uint64_t pendingH2D = 0;           // bytes uploaded by rtb_set_camera since the last render call (reported in its stats)
+    float msBuildSearchBvh = 0.0f;     // time spent building the search BVHs at create
     int levels = 1;                    // recursion levels a ray tree can have: maxRayDepth+1 if any object spawns children
     bool spawns = false;               // some object is Reflective / Transparent (their shade branches exist even when maxRayDepth == 0)
     int stackEntries = 1;              // per-thread traversal stack entries the kernels need for this scene
@@ -211,22 +214,51 @@ rt::Image uploadImage(RtbHandle* h, const RtbImage& im)
 // let the kernel evaluate the reference tree's eligibility rule for a single triangle.
 int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d, int meshIndex)
 {
+    const bool onDevice = h->createFlags & RTB_CREATE_DEVICE_BVH;
     rtpack::FastPath fp;
-    rtpack::packFastPath(m, fp);
-    if ((int)fp.nodes.size() > h->stagedNodesAll) {   // the largest search BVH is the one worth keeping in shared memory
-        h->stagedMeshIndex = meshIndex;
-        h->stagedNodesAll = (int)fp.nodes.size();
-        h->stagedTrisAll = (int)(fp.tris.size() / 3);
+    int maxDepth = 0, nNodes = 0, nTris = 0;
+    if (onDevice) {
+        // eligibility tables from the host (they restate the reference tree); the search BVH itself on the device
+        rtpack::packFastPath(m, fp, false);
+        float* dPos = nullptr;
+        CK(cudaMalloc((void**)&dPos, (size_t)m.nTris * 9 * sizeof(float)));
+        lbvh::DeviceBvh bvh;
+        cudaError_t e = cudaMemcpyAsync(dPos, m.pos, (size_t)m.nTris * 9 * sizeof(float), cudaMemcpyHostToDevice, h->ownStream);
+        if (e == cudaSuccess) e = lbvh::buildOnDevice(dPos, m.nTris, fp.lo, fp.hi, fp.pad, h->ownStream, bvh);
+        cudaFree(dPos);
+        if (e != cudaSuccess) throw CudaError{ e, "device search-BVH build" };
+        h->allocations.push_back(bvh.nodes);
+        h->allocations.push_back(bvh.tris);
+        d.bvhNodes = reinterpret_cast<const float4*>(bvh.nodes);
+        d.bvhTris = bvh.tris;
+        maxDepth = bvh.maxDepth; nNodes = bvh.nNodes; nTris = m.nTris;
+        h->msBuildSearchBvh += bvh.buildMs;
+        std::array<float, 6> b;
+        for (int a = 0; a < 3; ++a) { b[a] = fp.lo[a] - fp.pad; b[3 + a] = fp.hi[a] + fp.pad; }
+        // a NaN / inf vertex makes its triangle's box unbounded on the device too: no screen-space bound then
+        bool finite = true;
+        for (size_t i = 0; i < (size_t)m.nTris * 9; ++i) finite &= (m.pos[i] >= -FLT_MAX && m.pos[i] <= FLT_MAX);
+        if (finite) h->geomBounds.push_back(b); else h->unbounded = true;
+    } else {
+        const auto t0 = std::chrono::steady_clock::now();
+        rtpack::packFastPath(m, fp);
+        h->msBuildSearchBvh += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        d.bvhNodes = reinterpret_cast<const float4*>(upload(h, fp.nodes.data(), fp.nodes.size()));
+        d.bvhTris = upload(h, fp.tris.data(), fp.tris.size());
+        maxDepth = fp.maxDepth; nNodes = (int)fp.nodes.size(); nTris = (int)(fp.tris.size() / 3);
+        std::array<float, 6> b;
+        if (rtpack::meshBounds(fp, b)) h->geomBounds.push_back(b);
     }
-    if (fp.maxDepth > rtk::kStackDepth) throw std::runtime_error("search BVH deeper than the traversal stack (64)");
-    d.bvhNodes = reinterpret_cast<const float4*>(upload(h, fp.nodes.data(), fp.nodes.size()));
-    d.bvhTris = upload(h, fp.tris.data(), fp.tris.size());
+    if (maxDepth > rtk::kStackDepth) throw std::runtime_error("search BVH deeper than the traversal stack (64)");
+    if (nNodes > h->stagedNodesAll) {   // the largest search BVH is the one worth keeping in shared memory / prefetching
+        h->stagedMeshIndex = meshIndex;
+        h->stagedNodesAll = nNodes;
+        h->stagedTrisAll = nTris;
+    }
     d.triRefOff = upload(h, fp.triRefOff.data(), fp.triRefOff.size());
     d.triRefs = upload(h, fp.triRefs.data(), fp.triRefs.size());
     d.parent = upload(h, fp.parent.data(), fp.parent.size());
-    std::array<float, 6> b;
-    if (rtpack::meshBounds(fp, b)) h->geomBounds.push_back(b);
-    return fp.maxDepth;
+    return maxDepth;
 }
 
 void computePrimaryRect(RtbHandle* h)
@@ -374,7 +406,7 @@ void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk
 {
     const bool deep = h->spawns;
     const bool stats = h->createFlags & RTB_CREATE_WALK_STATS;
-    const bool staged = h->tileStaged && !stats && h->stagedNodes > 0;
+    const bool staged = h->tileStaged && !stats && h->stagedNodes > 0 && !(h->createFlags & RTB_CREATE_DEVICE_BVH);
     const size_t smem = staged ? rtk::tileSmemStagedOffset(kStagedGroups, h->stackEntries) + (size_t)h->stagedNodes * 64 + (size_t)h->stagedTris * 48
                                : tileSmemBytes(h);
     if (!staged && h->tileBlocksPerSm[genKind] == 0)
@@ -384,9 +416,11 @@ void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk
     // tile size: ONE 32-ray batch per warp of the group.  Measured on B200 (tools/gpu_sweep.sh, frame ms cfg1 / cfg3 / cfg4 /
     // dragon): 256 rays 0.49 / 0.92 / 0.46 / 1.39, 512 rays 0.55 / 0.99 / 0.51 / 1.44, 1024 rays 0.67 / 1.15 / 0.62 / 1.64 —
     // small tiles keep the groups of an SM out of phase and the dynamic tile cursor balances the SMs.
+    // Growing the tile when a rank of a multi-GPU frame has only 1-2 tiles per group (to save a "round") was measured too:
+    // 1/4 of cfg4's rows 0.277 -> 0.317 ms, 1/8 0.267 -> 0.285 ms (tools/gpu_strips.py): kept at one batch per warp.
     static const int forced = getenv("RTB_TILE_RAYS") ? atoi(getenv("RTB_TILE_RAYS")) : 0;
     long long R = forced > 0 ? forced : rtk::kTileThreads;
-    R = std::max<long long>(rtk::kTileThreads, std::min(1024LL, R)) & ~31LL;
+    R = std::max<long long>(32, std::min(1024LL, R)) & ~31LL;
     const int S = h->scene.shadowRaysPerHit;
     h->tileCapRays = std::max<long long>(h->tileCapRays, deep ? 2 * R : R);
     h->tileCapInterior = deep ? std::max<long long>(h->tileCapInterior, 4 * R) : 0;
@@ -509,6 +543,7 @@ void beginCall(RtbHandle* h)
 {
     CK(cudaSetDevice(h->device));
     h->stats = RtbStats{};
+    h->stats.msBuildSearchBvh = h->msBuildSearchBvh;
     h->stats.h2dBytes = h->pendingH2D;
     h->pendingH2D = 0;
     h->spans.clear();
@@ -744,6 +779,7 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
         const uint64_t h2d = h->stats.h2dBytes;
         resolveSpans(h);
         h->stats = RtbStats{};
+        h->stats.msBuildSearchBvh = h->msBuildSearchBvh;
         h->stats.h2dBytes = h2d;
     }
 
@@ -950,15 +986,6 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             h->stagedTris = (h->stagedNodes == h->stagedNodesAll && left >= (long long)h->stagedTrisAll * 48) ? h->stagedTrisAll : 0;
         }
         if (const char* e = getenv("RTB_TILE_STAGED")) h->tileStaged = atoi(e) != 0;
-        h->scene.areaPoints = upload(h, s->areaPoints, (size_t)s->nAreaPoints * 3);
-        if (s->flags & RTB_FLAG_USE_SKYBOX) {
-            // getSkybox indexes every face with one width / height (scene.cpp:381-442): six faces, all present, one size
-            for (int k = 0; k < 6; ++k)
-                if (!s->skybox[k].rgb || s->skybox[k].width <= 0 || s->skybox[k].height <= 0 || s->skybox[k].width != s->skybox[0].width
-                    || s->skybox[k].height != s->skybox[0].height)
-                    throw std::invalid_argument("RTB_FLAG_USE_SKYBOX needs six skybox faces of one size");
-            for (int k = 0; k < 6; ++k) h->scene.sky[k] = uploadImage(h, s->skybox[k]);
-        }
         // the header's resident copy (out-of-line device helpers read it): only now are all of its pointers final
         h->sceneDev = upload(h, &h->scene, 1);
         CK(cudaMallocHost(&h->scenePinned, sizeof(rt::Scene)));

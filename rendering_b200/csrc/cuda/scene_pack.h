@@ -58,6 +58,7 @@ struct FastPath {
     std::vector<int> parent;         // reference-tree parents
     int maxDepth = 0;
     int topNodes = 0;                // nodes [0, topNodes) are the tree's top levels in breadth-first order
+    float lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };   // finite bounds of the mesh's vertices
     float pad = 0;
 };
 
@@ -110,7 +111,9 @@ inline int reorderTopLevelsFirst(std::vector<rtbvh::Node>& nodes, int topBudget)
 
 constexpr int kTopLevelBudget = 2048;   // nodes of the breadth-first prefix (128 KB): what shared memory can hold next to the stacks
 
-inline void packFastPath(const RtbMesh& m, FastPath& out)
+// buildSearch = false: only the eligibility tables, the padding and the mesh bounds (the search BVH is then built on the
+// device, lbvh_build.cuh)
+inline void packFastPath(const RtbMesh& m, FastPath& out, bool buildSearch = true)
 {
     // padding: a hit accepted by the float Moller-Trumbore test lies within rounding distance of the
     // triangle; 1e-4 of the mesh diagonal is orders of magnitude above that
@@ -123,7 +126,9 @@ inline void packFastPath(const RtbMesh& m, FastPath& out)
     double diag2 = 0;
     for (int a = 0; a < 3; ++a) diag2 += hi[a] > lo[a] ? (double)(hi[a] - lo[a]) * (hi[a] - lo[a]) : 0.0;
     out.pad = (float)(1e-4 * std::sqrt(diag2)) + 1e-7f;
+    for (int a = 0; a < 3; ++a) { out.lo[a] = lo[a]; out.hi[a] = hi[a]; }
 
+    if (buildSearch) {
     rtbvh::Builder builder;
     int maxLeaf = 4;
     if (const char* e = std::getenv("RTB_BVH_LEAF")) maxLeaf = std::atoi(e);   // tuning knob
@@ -140,6 +145,7 @@ inline void packFastPath(const RtbMesh& m, FastPath& out)
         out.tris[k * 3 + 0] = float4{ p[0], p[1], p[2], triAsFloat };
         out.tris[k * 3 + 1] = float4{ p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f };   // v1 - v0 (objects.cpp:70)
         out.tris[k * 3 + 2] = float4{ p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f };   // v2 - v0 (objects.cpp:71)
+    }
     }
 
     out.parent.assign(m.nNodes, -1);
