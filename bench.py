@@ -241,10 +241,15 @@ def ours(args):
     exchange = (rdist.FrameExchange(h, w, args.strip_rows, rank, world, torch.device("cuda", local), args.transport, origin=r.strip_origin())
                 if world > 1 else None)
 
-    def step(rr):
+    def step(rr, end_event=None):
+        """One frame, device-resident result.  Everything is enqueued before the host waits: frame, exchange barrier (N > 1) and
+        the caller's closing event, so no host latency sits between the last kernel and the event."""
         if world == 1:
-            return rr.render_device(out.data_ptr(), stream=stream.cuda_stream), out
-        return exchange.render(rr, stream)
+            rr.render_device_begin(out.data_ptr(), stream=stream.cuda_stream)
+            if end_event is not None:
+                end_event.record(stream)
+            return rr.render_end(), out
+        return exchange.render(rr, stream, end_event)
 
     def barrier():
         torch.cuda.synchronize()
@@ -254,7 +259,7 @@ def ours(args):
 
     def timed_loop(rr, steps):
         """K frames, each bracketed by CUDA events on the render stream, L2 flushed (untimed) before each."""
-        total, launches = 0.0, 0
+        total, launches, dev_ms = 0.0, 0, 0.0
         kms = [0.0] * len(KERNEL_KINDS)
         kl = [0] * len(KERNEL_KINDS)
         last = None
@@ -262,18 +267,22 @@ def ours(args):
         for _ in range(steps):
             with torch.cuda.stream(stream):
                 flush.zero_()                      # evict L2 (256 MiB written, L2 is 126 MB); not timed
+            if exchange is not None:
+                exchange.align(stream)             # all ranks start the frame together (untimed device-side rendezvous)
+            with torch.cuda.stream(stream):
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            st, last = step(rr)
-            e1.record(stream)
+            st, last = step(rr, e1)
             e1.synchronize()
             total += e0.elapsed_time(e1)
+            dev_ms += st["msTotal"]              # this rank's own frame (fill .. output kernel), without the exchange
             launches += st["kernelLaunches"]
             for k in range(len(KERNEL_KINDS)):
                 kms[k] += st["msKernel"][k]
                 kl[k] += st["launchesKernel"][k]
         barrier()
+        timed_loop.rank_ms = dev_ms / steps
         return total, launches, kms, kl, st, last
 
     warm = max(args.warmup, 3)
@@ -284,6 +293,11 @@ def ours(args):
     sampler = ClockSampler(local)
     with sampler:
         total_ms, launches, _, _, fst, last_frame = timed_loop(r, args.steps)
+        per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+        per_rank[rank] = timed_loop.rank_ms
+        if world > 1:
+            dist.all_reduce(per_rank)
+        per_rank = [float(x) for x in per_rank.tolist()]
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -411,6 +425,7 @@ def ours(args):
                                 if world == 1 else f"per frame: camera uploaded on every rank, strips rendered, exchanged to rank 0 ({exchange.transport}), converted to BMP pixel bytes there and copied to pinned host memory; wall clock over all frames, no host barrier between frames")),
         "e2e_float": e2e["float"],
         "gpu_launches": launches, "launches_per_frame": launches / args.steps,
+        "per_rank_render_ms": per_rank,
         "roofline": {"bound": "hbm", "kernel": dom_name + (" (pass 1: ray generation, traversal, surface, shadow, shade of every tile)" if dom == k_tile else " (SSAA samples)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved and peak else None,
                      "traffic": traffic, "peak_source": peak_src, "avg_launch_ms": avg_launch_ms, "launches_per_step": dom_launches / ksteps,

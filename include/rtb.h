@@ -243,6 +243,14 @@ int  rtb_render_strips(RtbHandle* h, int stripRows, int rank, int worldSize, flo
  * then land in place through the output kernel's own stores and no separate gather or un-permute runs.  The caller
  * synchronises the ranks afterwards (a barrier).                                                                    */
 int  rtb_render_strips_to_frame(RtbHandle* h, int stripRows, int rank, int worldSize, float* frame, void* stream, RtbStats* stats);
+/* The same two calls split in halves for frame loops: *_begin plans the frame and ENQUEUES everything on the stream
+ * (kernels, output, counter read-back) without waiting; the caller may enqueue its own work behind it (the multi-GPU
+ * exchange barrier, the next frame's camera) and then calls rtb_render_end, which waits, re-runs the frame with larger
+ * queues in the rare overflow case, and returns the statistics.  One frame in flight per handle.  `fb` / `frame` must
+ * stay valid until rtb_render_end returns.                                                                          */
+int  rtb_render_begin(RtbHandle* h, int y0, int y1, float* fb, int fbOnDevice, void* stream);
+int  rtb_render_strips_to_frame_begin(RtbHandle* h, int stripRows, int rank, int worldSize, float* frame, void* stream);
+int  rtb_render_end(RtbHandle* h, RtbStats* stats);
 /* saveImage's conversion (see rtb_render_bgr8) of an assembled full float frame resident on the handle's device.    */
 int  rtb_frame_to_bgr8(RtbHandle* h, const float* frame, uint8_t* bgr, int onDevice, void* stream);
 /* Number of rows rank owns under that partition with the strips counted from row 0 (for sizing buffers: an upper

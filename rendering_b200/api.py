@@ -201,6 +201,20 @@ class Renderer:
                                                          C.c_void_p(stream) if stream else None, C.byref(st)))
         return st.as_dict()
 
+    # -- the same calls in halves: begin enqueues the frame without waiting, end waits and returns the statistics --
+    def render_device_begin(self, dev_ptr: int, y0: int = 0, y1: int | None = None, stream: int | None = None) -> None:
+        y1 = self.height if y1 is None else y1
+        self._check(self._lib.rtb_render_begin(self._h, y0, y1, C.c_void_p(dev_ptr), 1, C.c_void_p(stream) if stream else None))
+
+    def render_strips_to_frame_begin(self, frame_ptr: int, strip_rows: int, rank: int, world: int, stream: int | None = None) -> None:
+        self._check(self._lib.rtb_render_strips_to_frame_begin(self._h, strip_rows, rank, world, C.c_void_p(frame_ptr),
+                                                               C.c_void_p(stream) if stream else None))
+
+    def render_end(self) -> dict:
+        st = _ffi.RtbStats()
+        self._check(self._lib.rtb_render_end(self._h, C.byref(st)))
+        return st.as_dict()
+
     def frame_to_bgr8(self, frame_ptr: int, out: np.ndarray, stream: int | None = None) -> None:
         """saveImage's conversion of an assembled float frame on this handle's device into host pixel bytes."""
         assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == self.height * ((self.width * 3 + 3) & ~3)

@@ -78,7 +78,20 @@ struct QueueBufs {
 
 } // namespace
 
+enum OutputKind { OUT_FLOAT = 0, OUT_BGR8 = 1, OUT_SCATTER = 2 };   // OUT_SCATTER: rows go to their image position of a full-frame device buffer
+
 struct RtbHandle {
+    // the frame between rtb_render*_begin and rtb_render_end (beginRows / endRows)
+    struct FramePlan {
+        bool active = false;
+        cudaStream_t st = nullptr;
+        std::vector<int> owned;
+        void* fb = nullptr; float* pass1 = nullptr; int fbOnDevice = 0; OutputKind kind = OUT_FLOAT;
+        bool ssaa = false, literalWalk = false, culled = false;
+        int genX0 = 0, genCols = 0, nGenRows = 0, nInitRows = 0;
+        long long nPixels = 0, n0 = 0, interiorPixels = 0, flaggedCap = 0;
+        size_t outBytes = 0;
+    } plan;
     int device = 0;
     uint32_t createFlags = 0;
     cudaStream_t ownStream = nullptr;
@@ -559,10 +572,12 @@ float elapsed(cudaEvent_t a, cudaEvent_t b)
 
 // Reads the frame's counters back (the one synchronisation of a frame) and folds them into the stats.
 // Returns the overflow bits.
-int finishFrame(RtbHandle* h, cudaStream_t st, int passes)
+int finishFrame(RtbHandle* h, cudaStream_t st, int passes, bool enqueueReadback = false)
 {
-    CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
-    h->stats.d2hBytes += h->ctrBytes;
+    if (enqueueReadback) {
+        CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
+        h->stats.d2hBytes += h->ctrBytes;
+    }
     CK(cudaStreamSynchronize(st));
     const rtk::FrameCtr* fc = h->hFrame();
     const uint64_t S = (uint64_t)h->scene.shadowRaysPerHit;
@@ -607,8 +622,6 @@ void growAfterOverflow(RtbHandle* h, int bits, int passes)
     if (bits & rtk::OVF_INTERIORS) h->capInterior = std::max(2 * h->capInterior, (long long)h->hFrame()->interiors);
 }
 
-enum OutputKind { OUT_FLOAT = 0, OUT_BGR8 = 1, OUT_SCATTER = 2 };   // OUT_SCATTER: rows go to their image position of a full-frame device buffer
-
 void uploadRows(RtbHandle* h, cudaStream_t st, DevBuf& buf, std::vector<int>& resident, const std::vector<int>& rows)
 {
     if (rows == resident && buf.p) return;
@@ -620,36 +633,156 @@ void uploadRows(RtbHandle* h, cudaStream_t st, DevBuf& buf, std::vector<int>& re
     h->stats.h2dBytes += resident.size() * sizeof(int);
 }
 
-// Renders the rows in `owned` (ascending) into `out` (compact, owned rows in order).
-int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pass1, int fbOnDevice, void* stream, RtbStats* statsOut,
-    OutputKind kind = OUT_FLOAT)
+// ---- one frame (or a rank's rows of it) -----------------------------------------------------------------------------
+// A call is split in two so that a frame loop can keep the device busy: beginRows plans the frame and enqueues everything
+// (all kernels, the output copy, the counter read-back) on the stream WITHOUT waiting; endRows waits, reads the counters,
+// re-runs the frame with larger queues in the rare overflow case and fills the statistics.  The synchronous entry points
+// are begin + end; rtb_render*_begin / rtb_render_end expose the halves (a caller may enqueue its own work — e.g. the
+// multi-GPU exchange barrier — behind the frame before it waits).
+void enqueueAttempt(RtbHandle* h)
 {
+    RtbHandle::FramePlan& f = h->plan;
+    cudaStream_t st = f.st;
+    const rt::Scene& sc = h->scene;
+    const int w = sc.width, ht = sc.height;
+    const long long framePixels = (long long)w * ht;
+    const int* rect = h->primRect;
+    const std::vector<int>& owned = f.owned;
+
+    const long long level0 = std::max(f.n0, 4 * std::max(f.flaggedCap, h->capFlagged));
+    const bool tile = h->tilePipeline;
+    ensureCapacity(h, st, framePixels, level0, 2 * level0, 2 * level0, f.flaggedCap, !tile);
+    const int sampleBase = (int)framePixels;
+
+    CK(cudaEventRecord(h->ev[0], st));
+    if (f.nInitRows > 0) {
+        // culled: background colour where a primary ray would miss by construction; else Vec3f() zero-init (scene.cpp:599)
+        KernelSpan ks(h, st, RTB_K_RAYGEN);
+        // pixels that get a generated primary ray are written by pass 1 itself (hit or miss): skip them.  A listed row inside
+        // the rectangle's row range is always a pass-1 row when SSAA is on (initRows = pass-1 rows + the last image row).
+        const bool skip = f.ssaa && f.nGenRows > 0 && f.genCols > 0;
+        const int skipY0 = f.culled ? rect[2] : 0, skipY1 = f.culled ? rect[3] : ht - 1;
+        rtk::k_fill_background<<<gridFor(h, (long long)f.nInitRows * w), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, ht, h->rowsC.as<int>(),
+            f.nInitRows, f.culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f), skip ? f.genX0 : 0, skip ? f.genX0 + f.genCols : 0, skipY0, skip ? skipY1 : skipY0);
+        ks.done();
+    }
+    CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
+    if (f.n0 > 0) {
+        if (f.literalWalk) {   // the literal reference walk reads a materialised queue
+            KernelSpan ks(h, st, RTB_K_RAYGEN);
+            rtk::k_raygen<<<gridFor(h, f.n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), f.nGenRows, h->rays[0].view(), h->dLevel(0, 0));
+            ks.done();
+            enqueueLevels(h, st, 0, framePixels);
+        } else if (tile) {
+            enqueueTile(h, st, 0, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, -1, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev }, f.n0);
+        } else {
+            enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, 0, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev });
+        }
+    }
+    CK(cudaEventRecord(h->ev[1], st));
+
+    const bool contiguous = !owned.empty() && owned.back() - owned.front() + 1 == (int)owned.size();
+    auto emit = [&](void* dst, OutputKind k, size_t bytes) {
+        if (!dst || owned.empty()) return;
+        const bool direct = k == OUT_FLOAT && contiguous;   // the rows already lie contiguously in the slot array
+        void* target = dst;
+        if (!f.fbOnDevice && !direct) {
+            h->outStage.reserve(bytes, st, false);
+            target = h->outStage.p;
+        }
+        if (direct) {
+            const float* src = h->slots.as<float>() + (size_t)owned.front() * w * 3;
+            CK(cudaMemcpyAsync(dst, src, bytes, f.fbOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        } else {
+            KernelSpan ks(h, st, RTB_K_OUTPUT);
+            if (k == OUT_SCATTER)
+                rtk::k_scatter_rows<<<gridFor(h, (long long)(bytes / 16)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                    (int)owned.size(), static_cast<float*>(target));
+            else if (k == OUT_BGR8)
+                rtk::k_quantize_bgr8<<<gridFor(h, (long long)(bytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                    (int)owned.size(), static_cast<unsigned int*>(target));
+            else
+                rtk::k_gather_rows<<<gridFor(h, (long long)(bytes / 16)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                    (int)owned.size(), static_cast<float*>(target));
+            ks.done();
+            if (!f.fbOnDevice) CK(cudaMemcpyAsync(dst, target, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        if (!f.fbOnDevice) h->stats.d2hBytes += bytes;
+    };
+    if (f.pass1) emit(f.pass1, OUT_FLOAT, owned.size() * (size_t)w * 3 * sizeof(float));
+
+    if (f.ssaa) {
+        {
+            KernelSpan ks(h, st, RTB_K_SOBEL);
+            rtk::k_sobel<<<gridFor(h, f.interiorPixels), rtk::kBlock, 0, st>>>(w, ht, h->slots.as<float>(), h->rowsB.as<int>(),
+                (int)owned.size(), h->flagged.as<int>(), (int)h->capFlagged, h->dFrame());
+            ks.done();
+        }
+        CK(cudaEventRecord(h->ev[2], st));
+        if (f.literalWalk) {
+            KernelSpan ks(h, st, RTB_K_RAYGEN);
+            rtk::k_ssaa_gen<<<gridFor(h, 4 * h->capFlagged), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
+                h->rays[0].view(), h->dFrame(), h->dLevel(1, 0));
+            ks.done();
+            enqueueLevels(h, st, 1, framePixels);
+        } else if (tile) {
+            // the tile kernel also takes the mean of each pixel's 4 samples: no separate resolve
+            const long long hint = 4 * std::max(1024LL, h->flaggedSeen > 0 ? h->flaggedSeen : h->capFlagged / 4);
+            enqueueTile(h, st, 1, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, -1, 0, 0, h->slots.as<float>(), h->sceneDev },
+                std::min(hint, 4 * h->capFlagged));
+        } else {
+            enqueueLevels(h, st, 1, framePixels, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, sampleBase, 0, 0, h->slots.as<float>(), h->sceneDev });
+        }
+        if (!tile) {
+            KernelSpan ks(h, st, RTB_K_OUTPUT);
+            rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
+                h->slots.as<float>(), h->dFrame());
+            ks.done();
+        }
+    } else {
+        CK(cudaEventRecord(h->ev[2], st));
+    }
+    emit(f.fb, f.kind, f.outBytes);
+    CK(cudaEventRecord(h->ev[3], st));
+    // the frame's counters, read back behind everything else (endRows waits for them)
+    CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
+    h->stats.d2hBytes += h->ctrBytes;
+}
+
+// Plans the rows in `owned` (ascending) and enqueues the frame; output is compact (owned rows in order) unless kind == OUT_SCATTER.
+void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pass1, int fbOnDevice, void* stream, OutputKind kind)
+{
+    if (h->plan.active) throw std::runtime_error("a frame is already in flight on this handle: call rtb_render_end first");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
     beginCall(h);
     uploadSceneHeader(h, st);
     const rt::Scene& sc = h->scene;
     const int w = sc.width, ht = sc.height;
-    const long long framePixels = (long long)w * ht;
-    const bool ssaa = (sc.flags & rt::FLAG_SSAA) && !owned.empty();
+    RtbHandle::FramePlan& f = h->plan;
+    f = RtbHandle::FramePlan{};
+    f.st = st; f.owned = owned; f.fb = fb; f.pass1 = pass1; f.fbOnDevice = fbOnDevice; f.kind = kind;
+    f.ssaa = (sc.flags & rt::FLAG_SSAA) && !owned.empty();
 
     // pass-1 rows: owned rows plus a one-row halo for the Sobel window, minus the never-rendered last row
     std::vector<int> p1rows;
     {
         std::vector<char> need(ht, 0);
         for (int y : owned)
-            for (int dy = ssaa ? -1 : 0; dy <= (ssaa ? 1 : 0); ++dy)
+            for (int dy = f.ssaa ? -1 : 0; dy <= (f.ssaa ? 1 : 0); ++dy)
                 if (y + dy >= 0 && y + dy < ht - 1) need[y + dy] = 1;
         for (int y = 0; y < ht; ++y) if (need[y]) p1rows.push_back(y);
     }
     // primary rays are generated only inside the screen-space bounds of the geometry (computePrimaryRect); the pixels
     // outside are misses by construction and receive the background colour from k_fill_background
-    const bool literalWalk = h->createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK);
+    f.literalWalk = h->createFlags & (RTB_CREATE_COUNTERS | RTB_CREATE_EXACT_WALK);
     const int* rect = h->primRect;
-    const bool culled = !literalWalk && (rect[0] > 0 || rect[1] < w - 1 || rect[2] > 0 || rect[3] < ht - 1);
+    f.culled = !f.literalWalk && (rect[0] > 0 || rect[1] < w - 1 || rect[2] > 0 || rect[3] < ht - 1);
     std::vector<int> genRows;
-    if (culled) { for (int y : p1rows) if (y >= rect[2] && y < rect[3]) genRows.push_back(y); }
+    if (f.culled) { for (int y : p1rows) if (y >= rect[2] && y < rect[3]) genRows.push_back(y); }
     else genRows = p1rows;
-    const int genX0 = culled ? rect[0] : 0, genCols = culled ? rect[1] - rect[0] : w - 1;
+    f.genX0 = f.culled ? rect[0] : 0;
+    f.genCols = f.culled ? rect[1] - rect[0] : w - 1;
+    f.nGenRows = (int)genRows.size();
     uploadRows(h, st, h->rowsA, h->rowsAHost, genRows);
     uploadRows(h, st, h->rowsB, h->rowsBHost, owned);
     // rows this call initialises: what it renders plus what its Sobel windows read (incl. the never-rendered last row)
@@ -662,131 +795,45 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
                 if (y + dy >= 0 && y + dy < ht) need[y + dy] = 1;
         for (int y = 0; y < ht; ++y) if (need[y]) initRows.push_back(y);
     }
+    f.nInitRows = (int)initRows.size();
     uploadRows(h, st, h->rowsC, h->rowsCHost, initRows);
 
-    const long long nPixels = (long long)p1rows.size() * (w - 1);
-    const long long n0 = (!genRows.empty() && genCols > 0) ? rtk::raygenPaddedCount(genCols + 1, (int)genRows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
-    const long long interiorPixels = ssaa ? (long long)owned.size() * w : 0;
+    f.nPixels = (long long)p1rows.size() * (w - 1);
+    f.n0 = (!genRows.empty() && f.genCols > 0) ? rtk::raygenPaddedCount(f.genCols + 1, (int)genRows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
+    f.interiorPixels = f.ssaa ? (long long)owned.size() * w : 0;
     // SSAA capacity: what the last frame flagged plus head-room, at least 1/16 of the owned pixels; a frame that
     // flags more sets OVF_FLAGGED and is re-run with the exact count
-    long long flaggedCap = ssaa ? std::min(interiorPixels, std::max(interiorPixels / 16, h->flaggedSeen + h->flaggedSeen / 4 + 1024)) : 0;
+    f.flaggedCap = f.ssaa ? std::min(f.interiorPixels, std::max(f.interiorPixels / 16, h->flaggedSeen + h->flaggedSeen / 4 + 1024)) : 0;
     const size_t outRowBytes = kind == OUT_BGR8 ? (size_t)((w * 3 + 3) & ~3) : (size_t)w * 3 * sizeof(float);
-    const size_t outBytes = owned.size() * outRowBytes;
-    const bool contiguous = !owned.empty() && owned.back() - owned.front() + 1 == (int)owned.size();
+    f.outBytes = owned.size() * outRowBytes;
+    f.active = true;
+    enqueueAttempt(h);
+}
 
+int endRows(RtbHandle* h, RtbStats* statsOut)
+{
+    RtbHandle::FramePlan& f = h->plan;
+    if (!f.active) throw std::runtime_error("rtb_render_end without a frame in flight");
+    struct Done { RtbHandle::FramePlan& f; ~Done() { f.active = false; } } done{ f };
+    const int passes = f.ssaa ? 2 : 1;
     for (int attempt = 0;; ++attempt) {
-        const long long level0 = std::max(n0, 4 * std::max(flaggedCap, h->capFlagged));
-        const bool tile = h->tilePipeline;
-        ensureCapacity(h, st, framePixels, level0, 2 * level0, 2 * level0, flaggedCap, !tile);
-        const int sampleBase = (int)framePixels;
-
-        CK(cudaEventRecord(h->ev[0], st));
-        if (!initRows.empty()) {
-            // culled: background colour where a primary ray would miss by construction; else Vec3f() zero-init (scene.cpp:599)
-            KernelSpan ks(h, st, RTB_K_RAYGEN);
-            // pixels that get a generated primary ray are written by pass 1 itself (hit or miss): skip them.  A listed row inside
-            // the rectangle's row range is always a pass-1 row when SSAA is on (initRows = pass-1 rows + the last image row).
-            const bool skip = ssaa && !genRows.empty() && genCols > 0;
-            const int skipY0 = culled ? rect[2] : 0, skipY1 = culled ? rect[3] : ht - 1;
-            rtk::k_fill_background<<<gridFor(h, (long long)initRows.size() * w), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, ht, h->rowsC.as<int>(),
-                (int)initRows.size(), culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f), skip ? genX0 : 0, skip ? genX0 + genCols : 0, skipY0, skip ? skipY1 : skipY0);
-            ks.done();
-        }
-        CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
-        if (n0 > 0) {
-            if (literalWalk) {   // the literal reference walk reads a materialised queue
-                KernelSpan ks(h, st, RTB_K_RAYGEN);
-                rtk::k_raygen<<<gridFor(h, n0), rtk::kBlock, 0, st>>>(sc, h->rowsA.as<int>(), (int)genRows.size(), h->rays[0].view(), h->dLevel(0, 0));
-                ks.done();
-                enqueueLevels(h, st, 0, framePixels);
-            } else if (tile) {
-                enqueueTile(h, st, 0, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)genRows.size(), -1, genX0, genCols, h->slots.as<float>(), h->sceneDev }, n0);
-            } else {
-                enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), (int)genRows.size(), 0, genX0, genCols, h->slots.as<float>(), h->sceneDev });
-            }
-        }
-        CK(cudaEventRecord(h->ev[1], st));
-
-        auto emit = [&](void* dst, OutputKind k, size_t bytes) {
-            if (!dst || owned.empty()) return;
-            const bool direct = k == OUT_FLOAT && contiguous;   // the rows already lie contiguously in the slot array
-            void* target = dst;
-            if (!fbOnDevice && !direct) {
-                h->outStage.reserve(bytes, st, false);
-                target = h->outStage.p;
-            }
-            if (direct) {
-                const float* src = h->slots.as<float>() + (size_t)owned.front() * w * 3;
-                CK(cudaMemcpyAsync(dst, src, bytes, fbOnDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-            } else {
-                KernelSpan ks(h, st, RTB_K_OUTPUT);
-                if (k == OUT_SCATTER)
-                    rtk::k_scatter_rows<<<gridFor(h, (long long)(bytes / 16)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
-                        (int)owned.size(), static_cast<float*>(target));
-                else if (k == OUT_BGR8)
-                    rtk::k_quantize_bgr8<<<gridFor(h, (long long)(bytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
-                        (int)owned.size(), static_cast<unsigned int*>(target));
-                else
-                    rtk::k_gather_rows<<<gridFor(h, (long long)(bytes / 16)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
-                        (int)owned.size(), static_cast<float*>(target));
-                ks.done();
-                if (!fbOnDevice) CK(cudaMemcpyAsync(dst, target, bytes, cudaMemcpyDeviceToHost, st));
-            }
-            if (!fbOnDevice) h->stats.d2hBytes += bytes;
-        };
-        if (pass1) emit(pass1, OUT_FLOAT, owned.size() * (size_t)w * 3 * sizeof(float));
-
-        if (ssaa) {
-            {
-                KernelSpan ks(h, st, RTB_K_SOBEL);
-                rtk::k_sobel<<<gridFor(h, interiorPixels), rtk::kBlock, 0, st>>>(w, ht, h->slots.as<float>(), h->rowsB.as<int>(),
-                    (int)owned.size(), h->flagged.as<int>(), (int)h->capFlagged, h->dFrame());
-                ks.done();
-            }
-            CK(cudaEventRecord(h->ev[2], st));
-            if (literalWalk) {
-                KernelSpan ks(h, st, RTB_K_RAYGEN);
-                rtk::k_ssaa_gen<<<gridFor(h, 4 * h->capFlagged), rtk::kBlock, 0, st>>>(sc, h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
-                    h->rays[0].view(), h->dFrame(), h->dLevel(1, 0));
-                ks.done();
-                enqueueLevels(h, st, 1, framePixels);
-            } else if (tile) {
-                // the tile kernel also takes the mean of each pixel's 4 samples: no separate resolve
-                const long long hint = 4 * std::max(1024LL, h->flaggedSeen > 0 ? h->flaggedSeen : h->capFlagged / 4);
-                enqueueTile(h, st, 1, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, -1, 0, 0, h->slots.as<float>(), h->sceneDev },
-                    std::min(hint, 4 * h->capFlagged));
-            } else {
-                enqueueLevels(h, st, 1, framePixels, rtk::GEN_SSAA, rtk::GenArgs{ h->flagged.as<int>(), (int)h->capFlagged, sampleBase, 0, 0, h->slots.as<float>(), h->sceneDev });
-            }
-            if (!tile) {
-                KernelSpan ks(h, st, RTB_K_OUTPUT);
-                rtk::k_ssaa_resolve<<<gridFor(h, h->capFlagged), rtk::kBlock, 0, st>>>(h->flagged.as<int>(), (int)h->capFlagged, sampleBase,
-                    h->slots.as<float>(), h->dFrame());
-                ks.done();
-            }
-        } else {
-            CK(cudaEventRecord(h->ev[2], st));
-        }
-        emit(fb, kind, outBytes);
-        CK(cudaEventRecord(h->ev[3], st));
-
-        const int overflow = finishFrame(h, st, ssaa ? 2 : 1);
+        const int overflow = finishFrame(h, f.st, passes);
         if (!overflow) break;
         if (attempt >= 8 + h->levels) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queues still overflow after repeated growth" };
         // discard this attempt's statistics and run the frame again with larger queues
-        growAfterOverflow(h, overflow, ssaa ? 2 : 1);
-        flaggedCap = std::max(flaggedCap, h->capFlagged);
+        growAfterOverflow(h, overflow, passes);
+        f.flaggedCap = std::max(f.flaggedCap, h->capFlagged);
         const uint64_t h2d = h->stats.h2dBytes;
         resolveSpans(h);
         h->stats = RtbStats{};
         h->stats.msBuildSearchBvh = h->msBuildSearchBvh;
         h->stats.h2dBytes = h2d;
+        enqueueAttempt(h);
     }
-
     resolveSpans(h);
     h->flaggedSeen = (long long)h->stats.ssaaPixels;
-    h->stats.primaryRays = (uint64_t)nPixels + 4 * h->stats.ssaaPixels;
-    h->stats.backgroundPixels = (uint64_t)(nPixels - (culled ? (long long)genRows.size() * genCols : nPixels));
+    h->stats.primaryRays = (uint64_t)f.nPixels + 4 * h->stats.ssaaPixels;
+    h->stats.backgroundPixels = (uint64_t)(f.nPixels - (f.culled ? (long long)f.nGenRows * f.genCols : f.nPixels));
     h->stats.rays = h->stats.primaryRays + h->stats.secondaryRays + h->stats.shadowRays;
     h->stats.msPass1 = elapsed(h->ev[0], h->ev[1]);
     h->stats.msSobel = elapsed(h->ev[1], h->ev[2]);
@@ -794,6 +841,13 @@ int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     h->stats.msTotal = elapsed(h->ev[0], h->ev[3]);
     if (statsOut) *statsOut = h->stats;
     return RTB_OK;
+}
+
+int renderRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pass1, int fbOnDevice, void* stream, RtbStats* statsOut,
+    OutputKind kind = OUT_FLOAT)
+{
+    beginRows(h, owned, fb, pass1, fbOnDevice, stream, kind);
+    return endRows(h, statsOut);
 }
 
 // castRay / trace on caller-supplied rays: one pass, level-0 queue = the rays themselves
@@ -824,7 +878,7 @@ void enqueueUserRays(RtbHandle* h, cudaStream_t st, const float* rays, int nRays
                     rtk::SurfQueue{}, nullptr, h->dFrame(), h->dLevel(0, 0), rtk::GenArgs{});
             launchCheck();
         }
-        const int overflow = finishFrame(h, st, 1);
+        const int overflow = finishFrame(h, st, 1, true);
         if (!overflow) break;
         if (attempt >= 8 + h->levels) throw CudaError{ cudaErrorMemoryAllocation, "wavefront queues still overflow after repeated growth" };
         growAfterOverflow(h, overflow, 1);
@@ -1100,6 +1154,34 @@ int rtb_render_strips_to_frame(RtbHandle* h, int stripRowsN, int rank, int world
         const std::vector<int> rows = stripRows(h->scene.height, stripRowsN, rank, worldSize, stripOrigin(h));
         return renderRows(h, rows, frame, nullptr, 1, stream, stats, OUT_SCATTER);
     });
+}
+
+int rtb_render_begin(RtbHandle* h, int y0, int y1, float* fb, int fbOnDevice, void* stream)
+{
+    if (!h || !fb) { g_err = "null argument"; return RTB_ERR_ARG; }
+    if (y0 < 0 || y1 > h->scene.height || y0 > y1) { g_err = "row range outside the image"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        std::vector<int> rows;
+        for (int y = y0; y < y1; ++y) rows.push_back(y);
+        beginRows(h, rows, fb, nullptr, fbOnDevice, stream, OUT_FLOAT);
+        return RTB_OK;
+    });
+}
+
+int rtb_render_strips_to_frame_begin(RtbHandle* h, int stripRowsN, int rank, int worldSize, float* frame, void* stream)
+{
+    if (!h || !frame) { g_err = "null argument"; return RTB_ERR_ARG; }
+    if (stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) { g_err = "bad strip partition"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        beginRows(h, stripRows(h->scene.height, stripRowsN, rank, worldSize, stripOrigin(h)), frame, nullptr, 1, stream, OUT_SCATTER);
+        return RTB_OK;
+    });
+}
+
+int rtb_render_end(RtbHandle* h, RtbStats* stats)
+{
+    if (!h) { g_err = "null argument"; return RTB_ERR_ARG; }
+    return guarded([&]() { return endRows(h, stats); });
 }
 
 int rtb_frame_to_bgr8(RtbHandle* h, const float* frame, uint8_t* bgr, int onDevice, void* stream)

@@ -93,9 +93,20 @@ class FrameExchange:
                 if self.frame is None:
                     self.frame = torch.empty((height, width, 3), dtype=torch.float32, device=self.device)
 
-    def render(self, renderer, stream):
+    def align(self, stream):
+        """Device-side rendezvous of all ranks on `stream` (no data): lets a timing harness start every rank's frame together,
+        so that a frame's closing barrier does not absorb the ranks' start skew."""
+        if self.transport == "p2p":
+            with torch.cuda.stream(stream):
+                self.hdl.barrier(channel=1)
+        elif self.world > 1:
+            stream.synchronize()
+            dist.barrier()
+
+    def render(self, renderer, stream, end_event=None):
         """Render this rank's strips and exchange.  Returns (stats, frame on rank 0 / None elsewhere).  Everything is
-        enqueued on `stream` (a torch.cuda.Stream)."""
+        enqueued on `stream` (a torch.cuda.Stream); `end_event` (optional) is recorded behind the exchange, before the
+        host waits for the frame's statistics."""
         import contextlib
         on = (lambda: torch.cuda.stream(stream)) if self.device.type == "cuda" else contextlib.nullcontext
         raw = stream.cuda_stream if self.device.type == "cuda" else None
@@ -107,9 +118,13 @@ class FrameExchange:
             # stream must order itself before rank 0's next render() call.
             k = self.parity
             self.parity ^= 1
-            st = renderer.render_strips_to_frame(self.root_ptr + k * self.frame_bytes, self.strip, self.rank, self.world, stream=raw)
+            # the frame and its closing barrier are enqueued back to back; only then does the host wait for the frame's counters
+            renderer.render_strips_to_frame_begin(self.root_ptr + k * self.frame_bytes, self.strip, self.rank, self.world, stream=raw)
             with on():
                 self.hdl.barrier(channel=0)
+            if end_event is not None:
+                end_event.record(stream)
+            st = renderer.render_end()
             self.frame = self.frames[k]
             return st, (self.frame if self.rank == 0 else None)
         st = renderer.render_strips_device(self.local.data_ptr(), self.strip, self.rank, self.world, stream=raw)
@@ -118,4 +133,6 @@ class FrameExchange:
             if self.rank == 0:
                 for r in range(self.world):
                     self.frame.index_copy_(0, self.rows[r], self.bufs[r][: len(self.rows[r])])
+        if end_event is not None:
+            end_event.record(stream)
         return st, (self.frame if self.rank == 0 else None)

@@ -508,6 +508,34 @@ def test_strips_written_in_place_assemble_the_frame():
         assert np.array_equal(px, px_full)
 
 
+def test_begin_end_halves_render_the_same_frame_without_waiting_in_between():
+    # rtb_render_begin enqueues the whole frame and returns; the caller may put its own work behind it on the stream before
+    # rtb_render_end waits.  Same bits as the synchronous call, one frame in flight per handle, errors are loud.
+    sc = rb.Scene(text=MIXED_SCENE)
+    r = rb.Renderer(sc)
+    host, hs = r.render()
+    dev = torch.zeros((sc.height, sc.width, 3), dtype=torch.float32, device="cuda:0")
+    marker = torch.zeros(1, device="cuda:0")
+    stream = torch.cuda.Stream()
+    r.render_device_begin(dev.data_ptr(), stream=stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        marker += 1.0                                   # caller's own work behind the frame
+    with pytest.raises(rb.RtbError):
+        r.render_device_begin(dev.data_ptr(), stream=stream.cuda_stream)      # a frame is already in flight
+    st = r.render_end()
+    assert float(marker.item()) == 1.0
+    assert np.array_equal(dev.cpu().numpy().view(np.uint32), host.view(np.uint32))
+    assert st["rays"] == hs["rays"] and st["kernelLaunches"] == hs["kernelLaunches"]
+    with pytest.raises(rb.RtbError):
+        r.render_end()                                  # nothing in flight
+    # strips through the halves, and an overflow that has to re-run inside end (deep scene, tiny first queues)
+    frame = torch.full((sc.height, sc.width, 3), -1.0, dtype=torch.float32, device="cuda:0")
+    for rank in range(3):
+        r.render_strips_to_frame_begin(frame.data_ptr(), 5, rank, 3)
+        r.render_end()
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32), host.view(np.uint32))
+
+
 def test_device_buffer_path_matches_host_buffer_path():
     sc = rb.Scene(text=MIXED_SCENE)
     r = rb.Renderer(sc)
