@@ -1040,6 +1040,15 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             h->stagedTris = (h->stagedNodes == h->stagedNodesAll && left >= (long long)h->stagedTrisAll * 48) ? h->stagedTrisAll : 0;
         }
         if (const char* e = getenv("RTB_TILE_STAGED")) h->tileStaged = atoi(e) != 0;
+        h->scene.areaPoints = upload(h, s->areaPoints, (size_t)s->nAreaPoints * 3);
+        if (s->flags & RTB_FLAG_USE_SKYBOX) {
+            // getSkybox indexes every face with one width / height (scene.cpp:381-442): six faces, all present, one size
+            for (int k = 0; k < 6; ++k)
+                if (!s->skybox[k].rgb || s->skybox[k].width <= 0 || s->skybox[k].height <= 0 || s->skybox[k].width != s->skybox[0].width
+                    || s->skybox[k].height != s->skybox[0].height)
+                    throw std::invalid_argument("RTB_FLAG_USE_SKYBOX needs six skybox faces of one size");
+            for (int k = 0; k < 6; ++k) h->scene.sky[k] = uploadImage(h, s->skybox[k]);
+        }
         // the header's resident copy (out-of-line device helpers read it): only now are all of its pointers final
         h->sceneDev = upload(h, &h->scene, 1);
         CK(cudaMallocHost(&h->scenePinned, sizeof(rt::Scene)));
