@@ -461,6 +461,8 @@ void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk
     a.stagedTrisSrc = h->stagedTrisSrc;
     a.stagedNodes = h->stagedNodes;
     a.stagedTris = h->stagedTris;
+    static const int sortSurfaces = getenv("RTB_TILE_SORT") ? atoi(getenv("RTB_TILE_SORT")) : 0;
+    a.sortSurfaces = deep ? sortSurfaces : 0;
     KernelSpan ks(h, st, pass == 0 ? RTB_K_TILE : RTB_K_TILE_SSAA);
     if (staged) {
         if (genKind == rtk::GEN_PRIMARY) launchTileStaged<rtk::GEN_PRIMARY>(deep, h->stagedAttrSet[genKind], h->smemOptin, grid, smem, st, h->scene, a);

@@ -277,9 +277,21 @@ __global__ void __launch_bounds__(kBlock) k_trace(Scene sc, RayQueue q, int cap,
 // Threads `first`, `first + step`, ... of a group of `step` threads (a multiple of 32) share the work; `nSurf` is the
 // group's compaction counter (global memory for the frame-wide pipeline, shared memory for a tile).
 // MISSES = false compiles the miss branch (skybox lookup) out: rays generated inside the walk resolve their own misses.
+// Sort key of a hit for the tile pipeline's optional surface sort (north star: "secondary rays sorted by material / direction"):
+// material of the object hit (2 bits) and octant of the incoming ray's direction (3 bits).  Surfaces with one key sit next to
+// each other in the compacted queue, so a warp of the shade stage runs one material branch and the children it spawns — the
+// next level's queue — stay grouped by material and direction as well.
+__device__ __forceinline__ int surfaceSortKey(const Scene& sc, int obj, float4 d)
+{
+    return (sc.objects[obj].material & 3) * 8 + ((d.x < 0.f) ? 1 : 0) + ((d.y < 0.f) ? 2 : 0) + ((d.z < 0.f) ? 4 : 0);
+}
+
+// MISSES = false compiles the miss branch (skybox lookup) out: rays generated inside the walk resolve their own misses.
+// bins (tile pipeline, optional): 32 running slot counters, one per surfaceSortKey, pre-loaded with the bins' start offsets:
+// a surface takes the next slot of its bin instead of the next slot of the queue (counting sort).
 template <bool MISSES = true>
 __device__ __forceinline__ void surfaceStage(const Scene& sc, RayQueue q, HitQueue hits, SurfQueue surf, const Slots& slots, int n, int first, int step,
-    int* nSurf, int handleMisses)
+    int* nSurf, int handleMisses, int* bins = nullptr)
 {
     const int nPadded = (n + 31) & ~31;
     for (int i = first; i < nPadded; i += step) {
@@ -300,7 +312,9 @@ __device__ __forceinline__ void surfaceStage(const Scene& sc, RayQueue q, HitQue
                 else wantSurface = true;
             }
         }
-        const int si = warpAlloc(nSurf, wantSurface, 1);
+        int si;
+        if (bins) si = wantSurface ? atomicAdd(&bins[surfaceSortKey(sc, obj, q.d[i])], 1) : -1;
+        else si = warpAlloc(nSurf, wantSurface, 1);
         if (wantSurface) {
             surf.pS[si] = make_float4(s.P.x, s.P.y, s.P.z, s.specCoef);
             surf.nO[si] = make_float4(s.N.x, s.N.y, s.N.z, __int_as_float(obj));

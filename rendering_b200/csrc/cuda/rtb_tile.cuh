@@ -44,6 +44,7 @@ struct TileShared {
     int pad;
     TileLevelCtr lv[2];
     int levelEnd[kMaxTileLevels + 1];   // interior records handed out up to and including level l
+    int bins[32];                       // surface sort (optional): per-key counts, then running slot offsets
 };
 
 struct TileArgs {
@@ -65,6 +66,7 @@ struct TileArgs {
     const float4* stagedNodesSrc;  // nodes [0, stagedNodes): 4 x float4 each
     const float4* stagedTrisSrc;   // all leaf triangles (3 x float4 each) when stagedTris > 0
     int stagedNodes, stagedTris;
+    int sortSurfaces;              // deep scenes: counting-sort each level's surfaces by (material, direction octant)
 };
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (cp.async.bulk, SASS UBLKCP) ----
@@ -241,7 +243,28 @@ __global__ void __launch_bounds__(kTileThreads * NG, NG == 1 ? RTB_TILE_MIN_BLOC
                     // the other parity's counters are idle now: every thread has read the previous level's nNext before its walk
                     if (gtid == 0) gs.lv[(depth + 1) & 1] = TileLevelCtr{ 0u, 0u, 0, 0 };
                     // ---- surface records, hits compacted (castRay :762-775); misses of queued rays -> skybox ----
-                    surfaceStage<(DEEP || GEN == GEN_QUEUE)>(sc, q, ts.hits, ts.surf, slots, n, gtid, kTileThreads, &lc.nSurf, (depth > 0 || GEN == GEN_QUEUE) ? 1 : 0);
+                    int* bins = nullptr;
+                    if (DEEP && a.sortSurfaces && !showNormals) {
+                        // counting sort by (material, incoming direction octant): count, exclusive scan, then the surface stage
+                        // takes slots from its bin's running offset
+                        if (gtid < 32) gs.bins[gtid] = 0;
+                        groupSync<NG>(group);
+                        for (int i = gtid; i < n; i += kTileThreads) {
+                            const int obj = ts.hits.obj[i];
+                            if (obj >= 0) atomicAdd(&gs.bins[surfaceSortKey(sc, obj, q.d[i])], 1);
+                        }
+                        groupSync<NG>(group);
+                        if (gtid < 32) {
+                            const int own = gs.bins[gtid];
+                            int incl = own;
+                            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (gtid >= o) incl += v; }
+                            gs.bins[gtid] = incl - own;
+                            if (gtid == 31) lc.nSurf = incl;
+                        }
+                        groupSync<NG>(group);
+                        bins = gs.bins;
+                    }
+                    surfaceStage<(DEEP || GEN == GEN_QUEUE)>(sc, q, ts.hits, ts.surf, slots, n, gtid, kTileThreads, &lc.nSurf, (depth > 0 || GEN == GEN_QUEUE) ? 1 : 0, bins);
                     groupSync<NG>(group);
                     nSurf = lc.nSurf;
                     if (showNormals || S <= 0 || nSurf <= 0) break;
