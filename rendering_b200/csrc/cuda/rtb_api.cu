@@ -89,6 +89,8 @@ struct RtbHandle {
         void* fb = nullptr; float* pass1 = nullptr; int fbOnDevice = 0; OutputKind kind = OUT_FLOAT;
         bool ssaa = false, literalWalk = false, culled = false;
         int genX0 = 0, genCols = 0, nGenRows = 0, nInitRows = 0;
+        int nGenTiles = -1, nSkipTiles = 0;      // -1: rays for every 8x4 tile of the generation rectangle; else the kept / skipped lists
+        long long livePixels = 0;                // pixels that get a generated primary ray
         long long nPixels = 0, n0 = 0, interiorPixels = 0, flaggedCap = 0;
         size_t outBytes = 0;
     } plan;
@@ -108,6 +110,14 @@ struct RtbHandle {
     // world-space boxes (lo.xyz, hi.xyz) around everything a primary ray can hit, for the screen-space bounds of the
     // geometry; `unbounded` when a plane is present or misses need their direction (skybox)
     std::vector<std::array<float, 6>> geomBounds;
+    // finer boxes around the same geometry (search-BVH boxes a few levels down) and the screen coverage they project to:
+    // cover[y * cellsX + x / 8] != 0 where a primary ray can hit something; empty = no finer bound than primRect
+    std::vector<std::array<float, 6>> coverBounds;
+    std::vector<unsigned char> cover;
+    uint64_t cameraVersion = 1;        // bumped whenever primRect / cover are recomputed
+    uint64_t tileListCamera = 0;       // cameraVersion the resident tile lists (tilesKept / tilesSkipped) were built for
+    std::vector<int> tileListRows;     // ... and the generation rows
+    long long tileListLive = 0;        // live pixels of the kept tiles
     bool unbounded = false;
     int primRect[4] = { 0, 0, 0, 0 };  // pixel columns [x0,x1) and rows [y0,y1) primary rays are generated for
     uint64_t pendingH2D = 0;           // bytes uploaded by rtb_set_camera since the last render call (reported in its stats)
@@ -133,7 +143,7 @@ struct RtbHandle {
     bool stagedAttrSet[3] = { false, false, false };
 
     QueueBufs rays[2];
-    DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, rowsC, userRays, outStage;
+    DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, rowsC, userRays, outStage, tilesKept, tilesSkipped;
     DevBuf ctrBuf;                     // FrameCtr followed by 2 passes x (levels + 1) LevelCtr
     void* hCtr = nullptr;              // pinned mirror of ctrBuf
     size_t ctrBytes = 0;
@@ -147,7 +157,7 @@ struct RtbHandle {
     long long capSlots = 0;
     // SSAA capacity hint carried from frame to frame: flagged pixels seen last time
     long long flaggedSeen = 0;
-    std::vector<int> rowsAHost, rowsBHost, rowsCHost;   // row lists currently resident in rowsA / rowsB / rowsC
+    std::vector<int> rowsAHost, rowsBHost, rowsCHost, tilesKeptHost, tilesSkippedHost;   // lists currently resident in the DevBufs of the same name
 
     // per-kernel timing: (kind, start, stop) spans recorded on the render stream, resolved at the end of a call
     struct Span { int kind; cudaEvent_t a, b; };
@@ -251,7 +261,7 @@ int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d, int meshIndex)
         // a NaN / inf vertex makes its triangle's box unbounded on the device too: no screen-space bound then
         bool finite = true;
         for (size_t i = 0; i < (size_t)m.nTris * 9; ++i) finite &= (m.pos[i] >= -FLT_MAX && m.pos[i] <= FLT_MAX);
-        if (finite) h->geomBounds.push_back(b); else h->unbounded = true;
+        if (finite) { h->geomBounds.push_back(b); h->coverBounds.push_back(b); } else h->unbounded = true;
     } else {
         const auto t0 = std::chrono::steady_clock::now();
         rtpack::packFastPath(m, fp);
@@ -261,6 +271,7 @@ int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d, int meshIndex)
         maxDepth = fp.maxDepth; nNodes = (int)fp.nodes.size(); nTris = (int)(fp.tris.size() / 3);
         std::array<float, 6> b;
         if (rtpack::meshBounds(fp, b)) h->geomBounds.push_back(b);
+        rtpack::meshCoverBoxes(fp, 10, h->coverBounds);
     }
     if (maxDepth > rtk::kStackDepth) throw std::runtime_error("search BVH deeper than the traversal stack (64)");
     if (nNodes > h->stagedNodesAll) {   // the largest search BVH is the one worth keeping in shared memory / prefetching
@@ -276,7 +287,11 @@ int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d, int meshIndex)
 
 void computePrimaryRect(RtbHandle* h)
 {
-    rtpack::primaryRect(h->scene, h->geomBounds, h->unbounded, h->primRect);
+    static const bool noCover = getenv("RTB_NO_COVER") != nullptr;
+    const bool fine = !noCover && !h->coverBounds.empty();
+    rtpack::primaryRect(h->scene, fine ? h->coverBounds : h->geomBounds, h->unbounded, h->primRect, fine ? &h->cover : nullptr);
+    if (!fine) h->cover.clear();
+    h->cameraVersion++;
 }
 
 size_t stackBytes(const RtbHandle* h) { return (size_t)h->stackEntries * rtk::kBlock * sizeof(int); }
@@ -668,6 +683,12 @@ void enqueueAttempt(RtbHandle* h)
             f.nInitRows, f.culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f), skip ? f.genX0 : 0, skip ? f.genX0 + f.genCols : 0, skipY0, skip ? skipY1 : skipY0);
         ks.done();
     }
+    if (f.nSkipTiles > 0) {
+        KernelSpan ks(h, st, RTB_K_RAYGEN);
+        rtk::k_fill_tiles<<<gridFor(h, 32LL * f.nSkipTiles), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->tilesSkipped.as<int>(), f.nSkipTiles,
+            h->rowsA.as<int>(), f.nGenRows, f.genX0, f.genCols, sc.background);
+        ks.done();
+    }
     CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
     if (f.n0 > 0) {
         if (f.literalWalk) {   // the literal reference walk reads a materialised queue
@@ -676,9 +697,11 @@ void enqueueAttempt(RtbHandle* h)
             ks.done();
             enqueueLevels(h, st, 0, framePixels);
         } else if (tile) {
-            enqueueTile(h, st, 0, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, -1, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev }, f.n0);
+            enqueueTile(h, st, 0, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, -1, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev,
+                f.nGenTiles >= 0 ? h->tilesKept.as<int>() : nullptr, std::max(0, f.nGenTiles) }, f.n0);
         } else {
-            enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, 0, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev });
+            enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, 0, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev,
+                f.nGenTiles >= 0 ? h->tilesKept.as<int>() : nullptr, std::max(0, f.nGenTiles) });
         }
     }
     CK(cudaEventRecord(h->ev[1], st));
@@ -802,6 +825,39 @@ void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
 
     f.nPixels = (long long)p1rows.size() * (w - 1);
     f.n0 = (!genRows.empty() && f.genCols > 0) ? rtk::raygenPaddedCount(f.genCols + 1, (int)genRows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
+    f.livePixels = f.culled ? (long long)genRows.size() * f.genCols : f.nPixels;
+    if (f.culled && f.n0 > 0 && !h->cover.empty()) {
+        // Tiles of the generation rectangle that lie outside the projected coverage of the geometry get no rays at all.  The
+        // two lists only change with the camera or the rows: they stay resident between frames.
+        if (h->tileListCamera != h->cameraVersion || h->tileListRows != genRows) {
+            const int tilesX = (f.genCols + 7) / 8, tilesY = ((int)genRows.size() + 3) / 4, cellsX = (w + 7) / 8;
+            std::vector<int> kept, skipped;
+            std::vector<unsigned char> rowOr(cellsX);
+            long long live = 0;
+            for (int ty = 0; ty < tilesY; ++ty) {
+                std::fill(rowOr.begin(), rowOr.end(), 0);
+                const int r0 = ty * 4, r1 = std::min(r0 + 4, (int)genRows.size());
+                for (int rr = r0; rr < r1; ++rr) {
+                    const unsigned char* c = &h->cover[(size_t)genRows[rr] * cellsX];
+                    for (int cx = 0; cx < cellsX; ++cx) rowOr[cx] |= c[cx];
+                }
+                for (int tx = 0; tx < tilesX; ++tx) {
+                    const int xa = f.genX0 + tx * 8, xb = std::min(xa + 7, f.genX0 + f.genCols - 1);
+                    if (rowOr[xa / 8] | rowOr[xb / 8]) { kept.push_back(ty * tilesX + tx); live += (long long)(r1 - r0) * (xb - xa + 1); }
+                    else skipped.push_back(ty * tilesX + tx);
+                }
+            }
+            uploadRows(h, st, h->tilesKept, h->tilesKeptHost, kept);
+            uploadRows(h, st, h->tilesSkipped, h->tilesSkippedHost, skipped);
+            h->tileListCamera = h->cameraVersion;
+            h->tileListRows = genRows;
+            h->tileListLive = live;
+        }
+        f.nGenTiles = (int)h->tilesKeptHost.size();
+        f.nSkipTiles = (int)h->tilesSkippedHost.size();
+        f.n0 = 32LL * f.nGenTiles;
+        f.livePixels = h->tileListLive;
+    }
     f.interiorPixels = f.ssaa ? (long long)owned.size() * w : 0;
     // SSAA capacity: what the last frame flagged plus head-room, at least 1/16 of the owned pixels; a frame that
     // flags more sets OVF_FLAGGED and is re-run with the exact count
@@ -835,7 +891,7 @@ int endRows(RtbHandle* h, RtbStats* statsOut)
     resolveSpans(h);
     h->flaggedSeen = (long long)h->stats.ssaaPixels;
     h->stats.primaryRays = (uint64_t)f.nPixels + 4 * h->stats.ssaaPixels;
-    h->stats.backgroundPixels = (uint64_t)(f.nPixels - (f.culled ? (long long)f.nGenRows * f.genCols : f.nPixels));
+    h->stats.backgroundPixels = (uint64_t)(f.nPixels - f.livePixels);
     h->stats.rays = h->stats.primaryRays + h->stats.secondaryRays + h->stats.shadowRays;
     h->stats.msPass1 = elapsed(h->ev[0], h->ev[1]);
     h->stats.msSobel = elapsed(h->ev[1], h->ev[2]);
@@ -938,7 +994,7 @@ void destroyHandle(RtbHandle* h)
     for (void* p : h->allocations) cudaFree(p);
     h->rays[0].release(); h->rays[1].release();
     for (DevBuf* b : { &h->hitTuv, &h->hitObj, &h->surfP, &h->surfN, &h->surfC, &h->vis, &h->interiors, &h->slots, &h->flagged,
-             &h->rowsA, &h->rowsB, &h->rowsC, &h->userRays, &h->outStage, &h->tileSlab })
+             &h->rowsA, &h->rowsB, &h->rowsC, &h->userRays, &h->outStage, &h->tileSlab, &h->tilesKept, &h->tilesSkipped })
         b->release();
     h->ctrBuf.release();
     if (h->hCtr) cudaFreeHost(h->hCtr);
@@ -1008,7 +1064,11 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             if (m.nNodes > 0 && m.nTris > 0) h->stackEntries = std::max(h->stackEntries, buildFastPath(h, m, d, i) + 1);
             meshes.push_back(d);
         }
-        for (int i = 0; i < s->nObjects; ++i) rtpack::objectBounds(s->objects[i], h->geomBounds, h->unbounded);
+        for (int i = 0; i < s->nObjects; ++i) {
+            rtpack::objectBounds(s->objects[i], h->geomBounds, h->unbounded);
+            bool dummy = false;
+            rtpack::objectBounds(s->objects[i], h->coverBounds, dummy);
+        }
         computePrimaryRect(h);
         // recursion levels: only Reflective / Transparent hits spawn children (scene.cpp:854-941)
         bool spawns = false;

@@ -459,7 +459,13 @@ struct GenArgs {
                          // geometry; pixels outside were pre-filled with the background colour by k_fill_background)
     float* slots;        // frame-wide colour slots (misses of generated rays are resolved here)
     const Scene* scene;  // device-resident copy of the scene header for the out-of-line helpers below
+    const int* tiles;    // GEN_PRIMARY: the 8x4 pixel tiles (index into the cols x rows tile grid) rays are generated for, or nullptr
+    int nTiles;          //              = all of them; tiles outside the geometry's projected coverage are left to k_fill_tiles
 };
+__host__ __device__ inline long long primaryRayCount(const GenArgs& g)
+{
+    return g.tiles ? 32LL * g.nTiles : raygenPaddedCount(g.cols + 1, g.count);
+}
 
 // Kept out of line so their FP64 normalisation / cube-map code does not raise the register count of the
 // traversal loop (they run once per ray, the loop runs ~100 times).
@@ -549,7 +555,7 @@ __device__ __forceinline__ void walkRays(const bool ANY, const int GEN, const Sc
                     V3 o, d;
                     if (GEN == GEN_PRIMARY) {
                         const long long gmy = genOffset + my;
-                        const long long tile = gmy >> 5;
+                        const long long tile = gen.tiles ? (long long)__ldg(gen.tiles + (gmy >> 5)) : (gmy >> 5);
                         const int xr = (int)(tile % tilesX) * 8 + ((int)gmy & 7);
                         const int x = gen.x0 + xr;
                         const int rr = (int)(tile / tilesX) * 4 + (((int)gmy >> 3) & 3);
@@ -757,7 +763,7 @@ __global__ void __launch_bounds__(kBlock, RTB_WALK_MIN_BLOCKS) k_walk(Scene sc, 
     const int nSurfRaw = ANY ? lv->nSurf : 0;
     long long total;
     if (ANY) total = (long long)nSurfRaw * S;
-    else if (GEN == GEN_PRIMARY) total = raygenPaddedCount(gen.cols + 1, gen.count);
+    else if (GEN == GEN_PRIMARY) total = primaryRayCount(gen);
     else if (GEN == GEN_SSAA) total = 4LL * min(ctr->ssaaPixels, gen.count);
     else total = min(lv->nRays, cap);
     if (!ANY && GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) lv->nRays = (int)total;
@@ -1113,13 +1119,33 @@ __global__ void k_ssaa_resolve(const int* __restrict__ flagged, int flaggedCap, 
 __global__ void k_fill_background(float* __restrict__ fb, int width, int height, const int* __restrict__ rows, int nRows, V3 bg,
     int sx0, int sx1, int sy0, int sy1)
 {
-    const long long total = (long long)width * nRows;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / width), x = (int)(i - (long long)r * width);
+    // one CTA per listed row at a time: no per-pixel division, rows inside the skip range only touch their two margins
+    for (int r = blockIdx.x; r < nRows; r += gridDim.x) {
         const int y = rows[r];
-        if (x >= sx0 && x < sx1 && y >= sy0 && y < sy1) continue;
-        const bool rendered = x < width - 1 && y < height - 1;
-        storeSlot(fb, y * width + x, rendered ? bg : mk(0.0f, 0.0f, 0.0f));
+        const bool skipRow = y >= sy0 && y < sy1 && sx1 > sx0;
+        float* row = fb + (size_t)y * width * 3;
+        for (int x = threadIdx.x; x < width; x += blockDim.x) {
+            if (skipRow && x >= sx0 && x < sx1) {
+                if (sx1 - sx0 >= (int)blockDim.x) { x = ((sx1 - (int)threadIdx.x + (int)blockDim.x - 1) / (int)blockDim.x) * (int)blockDim.x + (int)threadIdx.x - (int)blockDim.x; }
+                continue;
+            }
+            const bool rendered = x < width - 1 && y < height - 1;
+            row[3 * x] = rendered ? bg.x : 0.0f; row[3 * x + 1] = rendered ? bg.y : 0.0f; row[3 * x + 2] = rendered ? bg.z : 0.0f;
+        }
+    }
+}
+
+// The 8x4 tiles inside the generation rectangle whose primary rays are NOT generated (outside the projected coverage of the
+// geometry, scene_pack.h primaryRect): their pixels are misses by construction -> background colour.  One warp per tile.
+__global__ void k_fill_tiles(float* __restrict__ fb, int width, const int* __restrict__ tiles, int nTiles, const int* __restrict__ rows, int nRows,
+    int x0, int cols, V3 bg)
+{
+    const int tilesX = (cols + 7) / 8;
+    const int lane = threadIdx.x & 31;
+    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nTiles; w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int tile = tiles[w];
+        const int xr = (tile % tilesX) * 8 + (lane & 7), rr = (tile / tilesX) * 4 + (lane >> 3);
+        if (xr < cols && rr < nRows) storeSlot(fb, rows[rr] * width + x0 + xr, bg);
     }
 }
 

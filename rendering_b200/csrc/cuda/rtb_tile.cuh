@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kTileThreads * NG, NG == 1 ? RTB_TILE_MIN_BLOC
     const Slots slots{ a.gen.slots, ts.localSlots };
 
     long long total;
-    if (GEN == GEN_PRIMARY) total = raygenPaddedCount(a.gen.cols + 1, a.gen.count);
+    if (GEN == GEN_PRIMARY) total = primaryRayCount(a.gen);
     else if (GEN == GEN_SSAA) total = 4LL * min(a.ctr->ssaaPixels, a.gen.count);
     else total = a.nUser;
     if (GEN != GEN_QUEUE && blockIdx.x == 0 && threadIdx.x == 0) a.lv[0].nRays = (int)min(total, 0x7fffffffLL);

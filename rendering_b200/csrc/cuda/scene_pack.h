@@ -170,10 +170,37 @@ inline void packFastPath(const RtbMesh& m, FastPath& out, bool buildSearch = tru
 // object, expanded by 2 pixels (the projection uses the camera constants in double; rounding is ~1e-4 pixel).
 // The whole rendered frame when anything is unbounded, behind / around the camera, or when missing rays need their
 // direction (skybox).  bounds: world-space boxes lo.xyz, hi.xyz around everything a primary ray can hit.
-inline void primaryRect(const rt::Scene& sc, const std::vector<std::array<float, 6>>& bounds, bool unbounded, int r[4])
+// cover (optional): per image row and 8-pixel column cell (cover[y * cellsX + x / 8], cellsX = (width + 7) / 8), 1 where the
+// projection of at least one box falls — with fine boxes (a mesh's search-BVH boxes a few levels down, meshCoverBoxes) the
+// primary rays of every 8x4 tile outside it are misses by construction and are not generated at all.
+inline bool pixelBoundsOfBox(const rt::Scene& sc, const std::array<float, 6>& b, double& minX, double& maxX, double& minY, double& maxY)
+{
+    minX = 1e300; maxX = -1e300; minY = 1e300; maxY = -1e300;
+    for (int c = 0; c < 8; ++c) {
+        const double v[3] = { (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, (double)b[(c & 4) ? 5 : 2] - sc.camPos.z };
+        if (!(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]))) return false;
+        // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
+        double cam[3];
+        for (int i = 0; i < 3; ++i) cam[i] = v[0] * sc.camM[i * 4 + 0] + v[1] * sc.camM[i * 4 + 1] + v[2] * sc.camM[i * 4 + 2];
+        const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (!(cam[2] < -1e-4 * len)) return false;                   // at or behind the camera plane: no bound
+        const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
+        // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
+        const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
+        const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
+        if (!(std::isfinite(px) && std::isfinite(py))) return false;
+        minX = std::min(minX, px); maxX = std::max(maxX, px);
+        minY = std::min(minY, py); maxY = std::max(maxY, py);
+    }
+    return true;
+}
+
+inline void primaryRect(const rt::Scene& sc, const std::vector<std::array<float, 6>>& bounds, bool unbounded, int r[4],
+    std::vector<unsigned char>* cover = nullptr)
 {
     const int wm1 = sc.width - 1, hm1 = sc.height - 1;
     r[0] = 0; r[1] = wm1; r[2] = 0; r[3] = hm1;
+    if (cover) cover->clear();
     if (unbounded || (sc.flags & rt::FLAG_SKYBOX)) return;
     // The projection below inverts rMatrix by transposing its 3x3 block, which is only right for what Camera::getRay builds
     // (a pure rotation, scene.cpp:24-48).  rtb_set_camera accepts any matrix through the C ABI: anything else — scale, shear,
@@ -187,30 +214,51 @@ inline void primaryRect(const rt::Scene& sc, const std::vector<std::array<float,
         if (sc.camM[i * 4 + 3] != 0.0f || sc.camM[3 * 4 + i] != 0.0f) return;
     }
     if (sc.camM[15] != 1.0f) return;
+    auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
+    const int cellsX = (sc.width + 7) / 8;
+    std::vector<unsigned char> cells;
+    if (cover) cells.assign((size_t)cellsX * sc.height, 0);
     double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
     for (const auto& b : bounds) {
-        for (int c = 0; c < 8; ++c) {
-            const double v[3] = { (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, (double)b[(c & 4) ? 5 : 2] - sc.camPos.z };
-            if (!(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]))) return;
-            // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
-            double cam[3];
-            for (int i = 0; i < 3; ++i) cam[i] = v[0] * sc.camM[i * 4 + 0] + v[1] * sc.camM[i * 4 + 1] + v[2] * sc.camM[i * 4 + 2];
-            const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-            if (!(cam[2] < -1e-4 * len)) return;                   // at or behind the camera plane: no bound
-            const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
-            // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
-            const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
-            const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
-            if (!(std::isfinite(px) && std::isfinite(py))) return;
-            minX = std::min(minX, px); maxX = std::max(maxX, px);
-            minY = std::min(minY, py); maxY = std::max(maxY, py);
+        double x0, x1, y0, y1;
+        if (!pixelBoundsOfBox(sc, b, x0, x1, y0, y1)) return;
+        minX = std::min(minX, x0); maxX = std::max(maxX, x1);
+        minY = std::min(minY, y0); maxY = std::max(maxY, y1);
+        if (cover) {
+            const int px0 = clampi(std::floor(x0) - 2, 0, wm1), px1 = clampi(std::ceil(x1) + 3, 0, wm1);
+            const int py0 = clampi(std::floor(y0) - 2, 0, hm1), py1 = clampi(std::ceil(y1) + 3, 0, hm1);
+            if (px1 > px0 && py1 > py0)
+                for (int y = py0; y < py1; ++y)
+                    std::memset(&cells[(size_t)y * cellsX + px0 / 8], 1, (size_t)((px1 - 1) / 8 - px0 / 8 + 1));
         }
     }
     if (bounds.empty()) { r[0] = r[1] = r[2] = r[3] = 0; return; }
-    auto clampi = [](double v, int lo, int hi) { return (int)std::max<double>(lo, std::min<double>(hi, v)); };
     r[0] = clampi(std::floor(minX) - 2, 0, wm1); r[1] = clampi(std::ceil(maxX) + 3, 0, wm1);
     r[2] = clampi(std::floor(minY) - 2, 0, hm1); r[3] = clampi(std::ceil(maxY) + 3, 0, hm1);
     if (r[1] <= r[0] || r[3] <= r[2]) r[0] = r[1] = r[2] = r[3] = 0;
+    if (cover) cover->swap(cells);
+}
+
+// Boxes that together contain a mesh: its search BVH's child boxes `depth` levels down (leaves stop earlier).  Finer than
+// the root box, so their projections hug the silhouette (primaryRect's `cover`).
+inline void meshCoverBoxes(const FastPath& fp, int depth, std::vector<std::array<float, 6>>& out)
+{
+    if (fp.nodes.empty() || fp.tris.empty()) return;
+    struct Item { int node, level; };
+    std::vector<Item> stack{ { 0, 0 } };
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const rtbvh::Node& n = fp.nodes[it.node];
+        const float* lo[2] = { n.c0lo, n.c1lo };
+        const float* hi[2] = { n.c0hi, n.c1hi };
+        const int child[2] = { n.child0, n.child1 };
+        for (int c = 0; c < 2; ++c) {
+            if (lo[c][0] > hi[c][0]) continue;                               // empty child
+            if (child[c] >= 0 && it.level + 1 < depth) stack.push_back({ child[c], it.level + 1 });
+            else out.push_back({ lo[c][0], lo[c][1], lo[c][2], hi[c][0], hi[c][1], hi[c][2] });
+        }
+    }
 }
 
 // The bounds primaryRect needs: the padded root box of a mesh's search BVH ...

@@ -77,6 +77,17 @@ def shim_primary_rect(scene):
     return tuple(rect)
 
 
+def shim_primary_cover(scene):
+    """-> ((x0, x1, y0, y1), cover or None): the tighter rectangle from the fine boxes and the per-row / 8-pixel-cell coverage mask"""
+    rect = (C.c_int * 4)()
+    cells_x = (scene.width + 7) // 8
+    cover = np.zeros((scene.height, cells_x), np.uint8)
+    lib = shim()
+    lib.shim_primary_cover.argtypes = [C.POINTER(_ffi.RtbScene), C.POINTER(C.c_int), C.c_void_p]
+    has = lib.shim_primary_cover(scene.view, rect, cover.ctypes.data)
+    return tuple(rect), (cover if has else None)
+
+
 def shim_render(scene, fast=False):
     h, w = scene.height, scene.width
     p1 = np.zeros((h, w, 3), np.float32)

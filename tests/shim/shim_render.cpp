@@ -212,6 +212,28 @@ int shim_primary_rect(const RtbScene* s, int rect[4])
     return 0;
 }
 
+// the finer bound rtb_create / rtb_set_camera compute the same way: cover[y * cellsX + x / 8] (cellsX = (width + 7) / 8) from the
+// search-BVH boxes 10 levels down; returns 1 when a coverage mask exists (cover filled), 0 when only the rectangle applies
+int shim_primary_cover(const RtbScene* s, int rect[4], unsigned char* cover)
+{
+    rt::Scene sc;
+    rtpack::packHeader(*s, sc);
+    std::vector<std::array<float, 6>> bounds;
+    bool unbounded = false;
+    for (int i = 0; i < s->nMeshes; ++i) {
+        if (s->meshes[i].nNodes == 0 || s->meshes[i].nTris == 0) continue;
+        rtpack::FastPath fp;
+        rtpack::packFastPath(s->meshes[i], fp);
+        rtpack::meshCoverBoxes(fp, 10, bounds);
+    }
+    for (int i = 0; i < s->nObjects; ++i) rtpack::objectBounds(s->objects[i], bounds, unbounded);
+    std::vector<unsigned char> cells;
+    rtpack::primaryRect(sc, bounds, unbounded, rect, &cells);
+    if (cells.empty()) return 0;
+    std::copy(cells.begin(), cells.end(), cover);
+    return 1;
+}
+
 } // extern "C"
 
 static int render_impl(const RtbScene* s, float* pass1, float* final, unsigned long long counters[4], bool fast)

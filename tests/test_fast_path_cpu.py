@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 
 import rendering_b200 as rb
-from helpers import shim, HAVE_ASSETS, MULTI_MESH_SCENE, diff_stats, golden_case, load, needs_assets, oracle_render, shim_primary_rect, shim_render, GOLDEN
+from helpers import (shim, HAVE_ASSETS, MULTI_MESH_SCENE, diff_stats, golden_case, load, needs_assets, oracle_render, shim_primary_cover, shim_primary_rect,
+                     shim_render, GOLDEN)
 
 
 @pytest.mark.parametrize("name", ["cfg2_128", "cfg4_240", "cfgD_160"])
@@ -64,6 +65,15 @@ def _check_rect(sc):
     ys, xs = np.nonzero(hit)
     if len(ys):
         assert xs.min() >= x0 and xs.max() < x1 and ys.min() >= y0 and ys.max() < y1, ((x0, x1, y0, y1), xs.min(), xs.max(), ys.min(), ys.max())
+    # the finer bound (search-BVH boxes 10 levels down): a tighter rectangle and a coverage mask per row and 8-pixel cell; every
+    # pixel whose primary ray hits something must lie in a covered cell of it, or the tile kernel would never generate its ray
+    (cx0, cx1, cy0, cy1), cover = shim_primary_cover(sc)
+    assert cx0 >= x0 and cx1 <= x1 and cy0 >= y0 and cy1 <= y1
+    if len(ys):
+        assert xs.min() >= cx0 and xs.max() < cx1 and ys.min() >= cy0 and ys.max() < cy1
+        if cover is not None:
+            assert cover[ys, xs // 8].all()
+            assert cover.sum() * 8 <= 4 * len(ys) + 64 * (cover.shape[0] + cover.shape[1]) or cover.mean() < 0.9      # it hugs the silhouette
     return (x0, x1, y0, y1), int(hit.sum())
 
 
