@@ -251,6 +251,13 @@ int  rtb_render_strips_to_frame(RtbHandle* h, int stripRows, int rank, int world
 int  rtb_render_begin(RtbHandle* h, int y0, int y1, float* fb, int fbOnDevice, void* stream);
 int  rtb_render_strips_to_frame_begin(RtbHandle* h, int stripRows, int rank, int worldSize, float* frame, void* stream);
 int  rtb_render_end(RtbHandle* h, RtbStats* stats);
+/* Frame loop with the output pipelined (camera sweeps): like rtb_render_bgr8 into a HOST buffer (pinned for a truly
+ * asynchronous copy), but the bytes leave on a second stream from one of two staging buffers, so the device-to-host copy
+ * of frame i overlaps the kernels of frame i+1.  rtb_render_end returns when the frame's kernels are done (statistics);
+ * the bytes of that frame are complete after rtb_output_sync (or after the rtb_render_end of the frame after next).
+ * Use at least two host buffers in turn.  Runs on the handle's own stream.                                          */
+int  rtb_render_bgr8_begin(RtbHandle* h, int y0, int y1, uint8_t* bgrHost);
+int  rtb_output_sync(RtbHandle* h);
 /* saveImage's conversion (see rtb_render_bgr8) of an assembled full float frame resident on the handle's device.    */
 int  rtb_frame_to_bgr8(RtbHandle* h, const float* frame, uint8_t* bgr, int onDevice, void* stream);
 /* Number of rows rank owns under that partition with the strips counted from row 0 (for sizing buffers: an upper

@@ -85,7 +85,7 @@ KERNEL_KINDS = ["raygen", "trace", "surface", "shadow", "shade", "combine", "sob
 # every symbol include/rtb.h declares, by library (tests check both lists against the header)
 HOST_SYMBOLS = ["rtb_scene_load", "rtb_scene_parse", "rtb_scene_view", "rtb_scene_image_name", "rtb_scene_free",
                 "rtb_scene_tree_stats", "rtb_camera_from_angles", "rtb_save_bmp", "rtb_save_bmp_bgr8", "rtb_host_last_error"]
-CUDA_SYMBOLS = ["rtb_create", "rtb_set_camera", "rtb_render", "rtb_render_bgr8", "rtb_render_ac", "rtb_render_strips", "rtb_render_strips_to_frame", "rtb_frame_to_bgr8", "rtb_strip_rows_owned", "rtb_strip_origin", "rtb_strip_rows", "rtb_render_begin", "rtb_render_strips_to_frame_begin", "rtb_render_end", "rtb_trace", "rtb_cast",
+CUDA_SYMBOLS = ["rtb_create", "rtb_set_camera", "rtb_render", "rtb_render_bgr8", "rtb_render_ac", "rtb_render_strips", "rtb_render_strips_to_frame", "rtb_frame_to_bgr8", "rtb_strip_rows_owned", "rtb_strip_origin", "rtb_strip_rows", "rtb_render_begin", "rtb_render_strips_to_frame_begin", "rtb_render_end", "rtb_render_bgr8_begin", "rtb_output_sync", "rtb_trace", "rtb_cast",
                 "rtb_device_of", "rtb_destroy", "rtb_last_error", "rtb_abi_version"]
 
 _host = None

@@ -210,6 +210,16 @@ class Renderer:
         self._check(self._lib.rtb_render_strips_to_frame_begin(self._h, strip_rows, rank, world, C.c_void_p(frame_ptr),
                                                                C.c_void_p(stream) if stream else None))
 
+    def render_bgr8_begin(self, out: np.ndarray, y0: int = 0, y1: int | None = None) -> None:
+        """Frame loop with pipelined output: enqueue the frame; its BMP pixel bytes arrive in `out` (host, ideally pinned) on a
+        second stream while the next frame renders.  render_end() returns the statistics; output_sync() waits for the bytes."""
+        y1 = self.height if y1 is None else y1
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == (y1 - y0) * ((self.width * 3 + 3) & ~3)
+        self._check(self._lib.rtb_render_bgr8_begin(self._h, y0, y1, out.ctypes.data))
+
+    def output_sync(self) -> None:
+        self._check(self._lib.rtb_output_sync(self._h))
+
     def render_end(self) -> dict:
         st = _ffi.RtbStats()
         self._check(self._lib.rtb_render_end(self._h, C.byref(st)))

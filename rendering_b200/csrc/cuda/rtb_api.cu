@@ -87,6 +87,7 @@ struct RtbHandle {
         cudaStream_t st = nullptr;
         std::vector<int> owned;
         void* fb = nullptr; float* pass1 = nullptr; int fbOnDevice = 0; OutputKind kind = OUT_FLOAT;
+        bool pipelinedCopy = false;      // OUT_BGR8 to a host buffer through copyStream (rtb_render_bgr8_begin)
         bool ssaa = false, literalWalk = false, culled = false;
         int genX0 = 0, genCols = 0, nGenRows = 0, nInitRows = 0;
         int nGenTiles = -1, nSkipTiles = 0;      // -1: rays for every 8x4 tile of the generation rectangle; else the kept / skipped lists
@@ -148,6 +149,12 @@ struct RtbHandle {
     void* hCtr = nullptr;              // pinned mirror of ctrBuf
     size_t ctrBytes = 0;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    // pipelined output (rtb_render_bgr8_begin): the frame's bytes leave on a second stream from one of two staging buffers, so
+    // the device-to-host copy of frame i overlaps the kernels of frame i+1
+    cudaStream_t copyStream = nullptr;
+    DevBuf pipeStage[2];
+    cudaEvent_t pipeReady[2] = { nullptr, nullptr }, pipeCopied[2] = { nullptr, nullptr };
+    int pipeParity = 0;
 
     // capacities (in items) the buffers above currently provide; grown on demand, never shrunk
     long long capLevel0 = 0;           // rays of a level-0 queue (ray generation)
@@ -767,7 +774,25 @@ void enqueueAttempt(RtbHandle* h)
     } else {
         CK(cudaEventRecord(h->ev[2], st));
     }
-    emit(f.fb, f.kind, f.outBytes);
+    if (f.pipelinedCopy && f.fb && !owned.empty()) {
+        // bytes -> staging buffer k on the render stream; the copy to the host runs on copyStream behind an event, and the render
+        // stream only waits for it again when buffer k is reused two frames later
+        const int k = h->pipeParity;
+        h->pipeParity ^= 1;
+        h->pipeStage[k].reserve(f.outBytes, st, false);
+        CK(cudaStreamWaitEvent(st, h->pipeCopied[k], 0));
+        KernelSpan ks(h, st, RTB_K_OUTPUT);
+        rtk::k_quantize_bgr8<<<gridFor(h, (long long)(f.outBytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+            (int)owned.size(), h->pipeStage[k].as<unsigned int>());
+        ks.done();
+        CK(cudaEventRecord(h->pipeReady[k], st));
+        CK(cudaStreamWaitEvent(h->copyStream, h->pipeReady[k], 0));
+        CK(cudaMemcpyAsync(f.fb, h->pipeStage[k].p, f.outBytes, cudaMemcpyDeviceToHost, h->copyStream));
+        CK(cudaEventRecord(h->pipeCopied[k], h->copyStream));
+        h->stats.d2hBytes += f.outBytes;
+    } else {
+        emit(f.fb, f.kind, f.outBytes);
+    }
     CK(cudaEventRecord(h->ev[3], st));
     // the frame's counters, read back behind everything else (endRows waits for them)
     CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
@@ -775,7 +800,7 @@ void enqueueAttempt(RtbHandle* h)
 }
 
 // Plans the rows in `owned` (ascending) and enqueues the frame; output is compact (owned rows in order) unless kind == OUT_SCATTER.
-void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pass1, int fbOnDevice, void* stream, OutputKind kind)
+void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pass1, int fbOnDevice, void* stream, OutputKind kind, bool pipelinedCopy = false)
 {
     if (h->plan.active) throw std::runtime_error("a frame is already in flight on this handle: call rtb_render_end first");
     cudaStream_t st = stream ? (cudaStream_t)stream : h->ownStream;
@@ -786,6 +811,7 @@ void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     RtbHandle::FramePlan& f = h->plan;
     f = RtbHandle::FramePlan{};
     f.st = st; f.owned = owned; f.fb = fb; f.pass1 = pass1; f.fbOnDevice = fbOnDevice; f.kind = kind;
+    f.pipelinedCopy = pipelinedCopy;
     f.ssaa = (sc.flags & rt::FLAG_SSAA) && !owned.empty();
 
     // pass-1 rows: owned rows plus a one-row halo for the Sobel window, minus the never-rendered last row
@@ -1000,6 +1026,12 @@ void destroyHandle(RtbHandle* h)
     if (h->hCtr) cudaFreeHost(h->hCtr);
     if (h->scenePinned) cudaFreeHost(h->scenePinned);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->copyStream) { cudaStreamSynchronize(h->copyStream); cudaStreamDestroy(h->copyStream); }
+    for (int k = 0; k < 2; ++k) {
+        if (h->pipeReady[k]) cudaEventDestroy(h->pipeReady[k]);
+        if (h->pipeCopied[k]) cudaEventDestroy(h->pipeCopied[k]);
+        h->pipeStage[k].release();
+    }
     for (cudaEvent_t e : h->eventPool) cudaEventDestroy(e);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
     delete h;
@@ -1035,6 +1067,11 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         h->smCount = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking));
         for (cudaEvent_t& e : h->ev) CK(cudaEventCreate(&e));
+        CK(cudaStreamCreateWithFlags(&h->copyStream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&h->pipeReady[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->pipeCopied[k], cudaEventDisableTiming));
+        }
 
         rtpack::packHeader(*s, h->scene);
         std::vector<rt::Object> objects;
@@ -1245,6 +1282,28 @@ int rtb_render_strips_to_frame_begin(RtbHandle* h, int stripRowsN, int rank, int
     if (stripRowsN <= 0 || worldSize <= 0 || rank < 0 || rank >= worldSize) { g_err = "bad strip partition"; return RTB_ERR_ARG; }
     return guarded([&]() {
         beginRows(h, stripRows(h->scene.height, stripRowsN, rank, worldSize, stripOrigin(h)), frame, nullptr, 1, stream, OUT_SCATTER);
+        return RTB_OK;
+    });
+}
+
+int rtb_render_bgr8_begin(RtbHandle* h, int y0, int y1, uint8_t* bgrHost)
+{
+    if (!h || !bgrHost) { g_err = "null argument"; return RTB_ERR_ARG; }
+    if (y0 < 0 || y1 > h->scene.height || y0 > y1) { g_err = "row range outside the image"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        std::vector<int> rows;
+        for (int y = y0; y < y1; ++y) rows.push_back(y);
+        beginRows(h, rows, bgrHost, nullptr, 0, nullptr, OUT_BGR8, true);
+        return RTB_OK;
+    });
+}
+
+int rtb_output_sync(RtbHandle* h)
+{
+    if (!h) { g_err = "null argument"; return RTB_ERR_ARG; }
+    return guarded([&]() {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->copyStream));
         return RTB_OK;
     });
 }

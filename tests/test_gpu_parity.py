@@ -536,6 +536,42 @@ def test_begin_end_halves_render_the_same_frame_without_waiting_in_between():
     assert np.array_equal(frame.cpu().numpy().view(np.uint32), host.view(np.uint32))
 
 
+def test_pipelined_output_delivers_every_frame_of_a_camera_sweep():
+    # rtb_render_bgr8_begin: the BMP bytes of frame i leave on a second stream while frame i+1 renders.  Every frame of a sweep
+    # must arrive intact in its own host buffer, equal to the synchronous call's bytes.
+    sc = rb.Scene(text=MIXED_SCENE)
+    r = rb.Renderer(sc)
+    cams = [((0.1 * i, 0.05 * i, 0.3), (2.0 * i, -3.0 * i, 0.0), 60.0) for i in range(6)]
+    want = []
+    for pos, rot, fov in cams:
+        r.set_camera(pos, rot, fov)
+        px, _ = r.render_bgr8()
+        want.append(px.copy())
+    assert any(not np.array_equal(want[0], w) for w in want[1:])
+    bufs = [torch.empty(want[0].shape, dtype=torch.uint8).pin_memory() for _ in range(len(cams))]
+    for i, (pos, rot, fov) in enumerate(cams):
+        r.set_camera(pos, rot, fov)
+        r.render_bgr8_begin(bufs[i].numpy())
+        st = r.render_end()
+        assert st["rays"] > 0
+    r.output_sync()
+    for i in range(len(cams)):
+        assert np.array_equal(bufs[i].numpy(), want[i]), i
+    # two buffers in turn, read one frame late (the documented use)
+    pair = [torch.empty(want[0].shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    got = []
+    for i, (pos, rot, fov) in enumerate(cams):
+        r.set_camera(pos, rot, fov)
+        r.render_bgr8_begin(pair[i & 1].numpy())
+        r.render_end()
+        if i >= 1:
+            r.output_sync() if i == 1 else None
+        if i >= 2:
+            pass
+    r.output_sync()
+    assert np.array_equal(pair[(len(cams) - 1) & 1].numpy(), want[-1]) and np.array_equal(pair[(len(cams) - 2) & 1].numpy(), want[-2])
+
+
 def test_device_buffer_path_matches_host_buffer_path():
     sc = rb.Scene(text=MIXED_SCENE)
     r = rb.Renderer(sc)
