@@ -153,6 +153,16 @@ def cuda_lib():
         lib.rtb_strip_origin.restype = C.c_int
         lib.rtb_strip_rows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         lib.rtb_strip_rows.restype = C.c_int
+        lib.rtb_render_begin.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
+        lib.rtb_render_begin.restype = C.c_int
+        lib.rtb_render_strips_to_frame_begin.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        lib.rtb_render_strips_to_frame_begin.restype = C.c_int
+        lib.rtb_render_end.argtypes = [vp, C.POINTER(RtbStats)]
+        lib.rtb_render_end.restype = C.c_int
+        lib.rtb_render_bgr8_begin.argtypes = [vp, C.c_int, C.c_int, vp]
+        lib.rtb_render_bgr8_begin.restype = C.c_int
+        lib.rtb_output_sync.argtypes = [vp]
+        lib.rtb_output_sync.restype = C.c_int
         lib.rtb_trace.argtypes = [vp, vp, C.c_int, vp, vp]
         lib.rtb_trace.restype = C.c_int
         lib.rtb_cast.argtypes = [vp, vp, C.c_int, vp]

@@ -215,7 +215,7 @@ class Renderer:
         second stream while the next frame renders.  render_end() returns the statistics; output_sync() waits for the bytes."""
         y1 = self.height if y1 is None else y1
         assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == (y1 - y0) * ((self.width * 3 + 3) & ~3)
-        self._check(self._lib.rtb_render_bgr8_begin(self._h, y0, y1, out.ctypes.data))
+        self._check(self._lib.rtb_render_bgr8_begin(self._h, y0, y1, C.c_void_p(out.ctypes.data)))
 
     def output_sync(self) -> None:
         self._check(self._lib.rtb_output_sync(self._h))
