@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 
 HOST_SOURCES = ["host/util.cpp", "host/objects.cpp", "host/scene.cpp", "host/flatten.cpp", "host/host_abi.cpp", "host/render.cpp"]
 CUDA_SOURCES = ["cuda/rtb_api.cu"]
-CUDA_DEPS = ["cuda/rtb_kernels.cuh", "cuda/rt_device.cuh", "cuda/scene_pack.h"]
+CUDA_DEPS = ["cuda/rtb_kernels.cuh", "cuda/rtb_tile.cuh", "cuda/rt_device.cuh", "cuda/scene_pack.h", "cuda/bvh_build.h", "cuda/lbvh_build.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]

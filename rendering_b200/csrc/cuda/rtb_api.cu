@@ -90,7 +90,10 @@ struct RtbHandle {
         bool pipelinedCopy = false;      // OUT_BGR8 to a host buffer through copyStream (rtb_render_bgr8_begin)
         bool ssaa = false, literalWalk = false, culled = false;
         int genX0 = 0, genCols = 0, nGenRows = 0, nInitRows = 0;
-        int nGenTiles = -1, nSkipTiles = 0;      // -1: rays for every 8x4 tile of the generation rectangle; else the kept / skipped lists
+        bool cover = false;                      // rays only for the 8x4 tiles of the resident kept list (k_tile_lists), the rest is filled
+        bool rebuildLists = false;               // ... and this frame (re)builds the lists: camera or rows changed
+        bool coverRead = false;                  // ... and reads their counters back (endRows)
+        int tilesTotal = 0;                      // tiles of the generation grid
         long long livePixels = 0;                // pixels that get a generated primary ray
         long long nPixels = 0, n0 = 0, interiorPixels = 0, flaggedCap = 0;
         size_t outBytes = 0;
@@ -111,14 +114,20 @@ struct RtbHandle {
     // world-space boxes (lo.xyz, hi.xyz) around everything a primary ray can hit, for the screen-space bounds of the
     // geometry; `unbounded` when a plane is present or misses need their direction (skybox)
     std::vector<std::array<float, 6>> geomBounds;
-    // finer boxes around the same geometry (search-BVH boxes a few levels down) and the screen coverage they project to:
-    // cover[y * cellsX + x / 8] != 0 where a primary ray can hit something; empty = no finer bound than primRect
+    // finer boxes around the same geometry (search-BVH boxes a few levels down), resident on the device: every frame whose
+    // camera or rows changed projects them into a coverage bitmap and turns that into the kept / skipped tile lists
+    // (k_cover_mark, k_tile_lists) without the host touching a pixel; empty = no finer bound than primRect
     std::vector<std::array<float, 6>> coverBounds;
-    std::vector<unsigned char> cover;
-    uint64_t cameraVersion = 1;        // bumped whenever primRect / cover are recomputed
+    const float* coverBoxesDev = nullptr;
+    int nCoverBoxes = 0;
+    DevBuf coverBits;
+    rtk::CoverCtr* coverCtrDev = nullptr;
+    rtk::CoverCtr* hCover = nullptr;   // pinned mirror, read back by the frames that rebuild the lists
+    uint64_t cameraVersion = 1;        // bumped whenever the camera (hence primRect / the coverage) changes
     uint64_t tileListCamera = 0;       // cameraVersion the resident tile lists (tilesKept / tilesSkipped) were built for
     std::vector<int> tileListRows;     // ... and the generation rows
-    long long tileListLive = 0;        // live pixels of the kept tiles
+    long long tileListLive = -1;       // live pixels / length of the kept list as last read back (-1: not known yet)
+    int tileListKept = -1;
     bool unbounded = false;
     int primRect[4] = { 0, 0, 0, 0 };  // pixel columns [x0,x1) and rows [y0,y1) primary rays are generated for
     uint64_t pendingH2D = 0;           // bytes uploaded by rtb_set_camera since the last render call (reported in its stats)
@@ -164,7 +173,7 @@ struct RtbHandle {
     long long capSlots = 0;
     // SSAA capacity hint carried from frame to frame: flagged pixels seen last time
     long long flaggedSeen = 0;
-    std::vector<int> rowsAHost, rowsBHost, rowsCHost, tilesKeptHost, tilesSkippedHost;   // lists currently resident in the DevBufs of the same name
+    std::vector<int> rowsAHost, rowsBHost, rowsCHost;   // lists currently resident in the DevBufs of the same name
 
     // per-kernel timing: (kind, start, stop) spans recorded on the render stream, resolved at the end of a call
     struct Span { int kind; cudaEvent_t a, b; };
@@ -294,10 +303,8 @@ int buildFastPath(RtbHandle* h, const RtbMesh& m, rt::Mesh& d, int meshIndex)
 
 void computePrimaryRect(RtbHandle* h)
 {
-    static const bool noCover = getenv("RTB_NO_COVER") != nullptr;
-    const bool fine = !noCover && !h->coverBounds.empty();
-    rtpack::primaryRect(h->scene, fine ? h->coverBounds : h->geomBounds, h->unbounded, h->primRect, fine ? &h->cover : nullptr);
-    if (!fine) h->cover.clear();
+    // the rectangle comes from the few root boxes (host, microseconds); the fine coverage inside it is the device's job
+    rtpack::primaryRect(h->scene, h->geomBounds, h->unbounded, h->primRect);
     h->cameraVersion++;
 }
 
@@ -690,9 +697,22 @@ void enqueueAttempt(RtbHandle* h)
             f.nInitRows, f.culled ? sc.background : rt::mk(0.0f, 0.0f, 0.0f), skip ? f.genX0 : 0, skip ? f.genX0 + f.genCols : 0, skipY0, skip ? skipY1 : skipY0);
         ks.done();
     }
-    if (f.nSkipTiles > 0) {
+    if (f.cover) {
         KernelSpan ks(h, st, RTB_K_RAYGEN);
-        rtk::k_fill_tiles<<<gridFor(h, 32LL * f.nSkipTiles), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->tilesSkipped.as<int>(), f.nSkipTiles,
+        if (f.rebuildLists) {
+            const int cellsX = (w + 7) / 8;
+            CK(cudaMemsetAsync(h->coverBits.p, 0, (size_t)ht * ((cellsX + 31) / 32) * sizeof(unsigned), st));
+            CK(cudaMemsetAsync(h->coverCtrDev, 0, sizeof(rtk::CoverCtr), st));
+            rtk::k_cover_mark<<<gridFor(h, 32LL * h->nCoverBoxes), rtk::kBlock, 0, st>>>(h->sceneDev, h->coverBoxesDev, h->nCoverBoxes,
+                h->coverBits.as<unsigned>(), cellsX, h->coverCtrDev);
+            rtk::k_tile_lists<<<gridFor(h, f.tilesTotal), rtk::kBlock, 0, st>>>(h->coverBits.as<unsigned>(), cellsX, h->rowsA.as<int>(), f.nGenRows,
+                f.genX0, f.genCols, h->tilesKept.as<int>(), h->tilesSkipped.as<int>(), h->coverCtrDev);
+            CK(cudaMemcpyAsync(h->hCover, h->coverCtrDev, sizeof(rtk::CoverCtr), cudaMemcpyDeviceToHost, st));
+            h->stats.d2hBytes += sizeof(rtk::CoverCtr);
+            f.rebuildLists = false;   // a re-run after a queue overflow finds the lists resident
+            f.coverRead = true;
+        }
+        rtk::k_fill_tiles<<<gridFor(h, 32LL * f.tilesTotal), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->tilesSkipped.as<int>(), h->coverCtrDev,
             h->rowsA.as<int>(), f.nGenRows, f.genX0, f.genCols, sc.background);
         ks.done();
     }
@@ -705,10 +725,10 @@ void enqueueAttempt(RtbHandle* h)
             enqueueLevels(h, st, 0, framePixels);
         } else if (tile) {
             enqueueTile(h, st, 0, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, -1, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev,
-                f.nGenTiles >= 0 ? h->tilesKept.as<int>() : nullptr, std::max(0, f.nGenTiles) }, f.n0);
+                f.cover ? h->tilesKept.as<int>() : nullptr, f.cover ? &h->coverCtrDev->nKept : nullptr }, f.n0);
         } else {
             enqueueLevels(h, st, 0, framePixels, rtk::GEN_PRIMARY, rtk::GenArgs{ h->rowsA.as<int>(), f.nGenRows, 0, f.genX0, f.genCols, h->slots.as<float>(), h->sceneDev,
-                f.nGenTiles >= 0 ? h->tilesKept.as<int>() : nullptr, std::max(0, f.nGenTiles) });
+                f.cover ? h->tilesKept.as<int>() : nullptr, f.cover ? &h->coverCtrDev->nKept : nullptr });
         }
     }
     CK(cudaEventRecord(h->ev[1], st));
@@ -852,37 +872,26 @@ void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     f.nPixels = (long long)p1rows.size() * (w - 1);
     f.n0 = (!genRows.empty() && f.genCols > 0) ? rtk::raygenPaddedCount(f.genCols + 1, (int)genRows.size()) : 0;   // whole 8x4 tiles, padding lanes idle
     f.livePixels = f.culled ? (long long)genRows.size() * f.genCols : f.nPixels;
-    if (f.culled && f.n0 > 0 && !h->cover.empty()) {
+    static const bool noCover = getenv("RTB_NO_COVER") != nullptr;
+    if (f.culled && f.n0 > 0 && h->nCoverBoxes > 0 && !noCover) {
         // Tiles of the generation rectangle that lie outside the projected coverage of the geometry get no rays at all.  The
-        // two lists only change with the camera or the rows: they stay resident between frames.
+        // two lists are built ON THE DEVICE by this frame's first kernels whenever the camera or the rows changed (a camera
+        // sweep costs the host nothing) and stay resident otherwise; the host sizes grids with the grid's tile count and
+        // learns the kept count / live pixels from the counter read-back.
+        const int tilesX = (f.genCols + 7) / 8, tilesY = ((int)genRows.size() + 3) / 4, cellsX = (w + 7) / 8;
+        f.cover = true;
+        f.tilesTotal = tilesX * tilesY;
         if (h->tileListCamera != h->cameraVersion || h->tileListRows != genRows) {
-            const int tilesX = (f.genCols + 7) / 8, tilesY = ((int)genRows.size() + 3) / 4, cellsX = (w + 7) / 8;
-            std::vector<int> kept, skipped;
-            std::vector<unsigned char> rowOr(cellsX);
-            long long live = 0;
-            for (int ty = 0; ty < tilesY; ++ty) {
-                std::fill(rowOr.begin(), rowOr.end(), 0);
-                const int r0 = ty * 4, r1 = std::min(r0 + 4, (int)genRows.size());
-                for (int rr = r0; rr < r1; ++rr) {
-                    const unsigned char* c = &h->cover[(size_t)genRows[rr] * cellsX];
-                    for (int cx = 0; cx < cellsX; ++cx) rowOr[cx] |= c[cx];
-                }
-                for (int tx = 0; tx < tilesX; ++tx) {
-                    const int xa = f.genX0 + tx * 8, xb = std::min(xa + 7, f.genX0 + f.genCols - 1);
-                    if (rowOr[xa / 8] | rowOr[xb / 8]) { kept.push_back(ty * tilesX + tx); live += (long long)(r1 - r0) * (xb - xa + 1); }
-                    else skipped.push_back(ty * tilesX + tx);
-                }
-            }
-            uploadRows(h, st, h->tilesKept, h->tilesKeptHost, kept);
-            uploadRows(h, st, h->tilesSkipped, h->tilesSkippedHost, skipped);
+            f.rebuildLists = true;
+            h->coverBits.reserve((size_t)ht * ((cellsX + 31) / 32) * sizeof(unsigned), st, false);
+            h->tilesKept.reserve((size_t)f.tilesTotal * sizeof(int), st, false);
+            h->tilesSkipped.reserve((size_t)f.tilesTotal * sizeof(int), st, false);
             h->tileListCamera = h->cameraVersion;
             h->tileListRows = genRows;
-            h->tileListLive = live;
+            h->tileListLive = -1;
+            h->tileListKept = -1;
         }
-        f.nGenTiles = (int)h->tilesKeptHost.size();
-        f.nSkipTiles = (int)h->tilesSkippedHost.size();
-        f.n0 = 32LL * f.nGenTiles;
-        f.livePixels = h->tileListLive;
+        f.n0 = 32LL * (h->tileListKept >= 0 ? h->tileListKept : f.tilesTotal);
     }
     f.interiorPixels = f.ssaa ? (long long)owned.size() * w : 0;
     // SSAA capacity: what the last frame flagged plus head-room, at least 1/16 of the owned pixels; a frame that
@@ -917,6 +926,10 @@ int endRows(RtbHandle* h, RtbStats* statsOut)
     resolveSpans(h);
     h->flaggedSeen = (long long)h->stats.ssaaPixels;
     h->stats.primaryRays = (uint64_t)f.nPixels + 4 * h->stats.ssaaPixels;
+    if (f.cover) {
+        if (f.coverRead) { h->tileListLive = h->hCover->livePixels; h->tileListKept = h->hCover->nKept; }
+        f.livePixels = h->tileListLive;
+    }
     h->stats.backgroundPixels = (uint64_t)(f.nPixels - f.livePixels);
     h->stats.rays = h->stats.primaryRays + h->stats.secondaryRays + h->stats.shadowRays;
     h->stats.msPass1 = elapsed(h->ev[0], h->ev[1]);
@@ -1020,10 +1033,11 @@ void destroyHandle(RtbHandle* h)
     for (void* p : h->allocations) cudaFree(p);
     h->rays[0].release(); h->rays[1].release();
     for (DevBuf* b : { &h->hitTuv, &h->hitObj, &h->surfP, &h->surfN, &h->surfC, &h->vis, &h->interiors, &h->slots, &h->flagged,
-             &h->rowsA, &h->rowsB, &h->rowsC, &h->userRays, &h->outStage, &h->tileSlab, &h->tilesKept, &h->tilesSkipped })
+             &h->rowsA, &h->rowsB, &h->rowsC, &h->userRays, &h->outStage, &h->tileSlab, &h->tilesKept, &h->tilesSkipped, &h->coverBits })
         b->release();
     h->ctrBuf.release();
     if (h->hCtr) cudaFreeHost(h->hCtr);
+    if (h->hCover) cudaFreeHost(h->hCover);
     if (h->scenePinned) cudaFreeHost(h->scenePinned);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     if (h->copyStream) { cudaStreamSynchronize(h->copyStream); cudaStreamDestroy(h->copyStream); }
@@ -1105,6 +1119,15 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
             rtpack::objectBounds(s->objects[i], h->geomBounds, h->unbounded);
             bool dummy = false;
             rtpack::objectBounds(s->objects[i], h->coverBounds, dummy);
+        }
+        if (!h->coverBounds.empty() && !h->unbounded) {
+            h->coverBoxesDev = upload(h, &h->coverBounds[0][0], h->coverBounds.size() * 6);
+            h->nCoverBoxes = (int)h->coverBounds.size();
+            void* c = nullptr;
+            CK(cudaMalloc(&c, sizeof(rtk::CoverCtr)));
+            h->allocations.push_back(c);
+            h->coverCtrDev = static_cast<rtk::CoverCtr*>(c);
+            CK(cudaMallocHost(&h->hCover, sizeof(rtk::CoverCtr)));
         }
         computePrimaryRect(h);
         // recursion levels: only Reflective / Transparent hits spawn children (scene.cpp:854-941)

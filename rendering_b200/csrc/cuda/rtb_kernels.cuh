@@ -24,6 +24,9 @@
 // the rest is bump-allocated for SSAA samples and for the children of Reflective / Transparent hits.
 // Every ray carries the slot its colour must land in, so queue order never affects the image.
 #pragma once
+#ifndef RTB_HOIST_NODES
+#define RTB_HOIST_NODES 1
+#endif
 
 #include <cuda_runtime.h>
 
@@ -460,11 +463,12 @@ struct GenArgs {
     float* slots;        // frame-wide colour slots (misses of generated rays are resolved here)
     const Scene* scene;  // device-resident copy of the scene header for the out-of-line helpers below
     const int* tiles;    // GEN_PRIMARY: the 8x4 pixel tiles (index into the cols x rows tile grid) rays are generated for, or nullptr
-    int nTiles;          //              = all of them; tiles outside the geometry's projected coverage are left to k_fill_tiles
+    const int* nTiles;   //              = all of them; the list and its length live on the device (k_tile_lists): tiles outside the
+                         //              geometry's projected coverage get the background colour from k_fill_tiles instead of rays
 };
-__host__ __device__ inline long long primaryRayCount(const GenArgs& g)
+__device__ __forceinline__ long long primaryRayCount(const GenArgs& g)
 {
-    return g.tiles ? 32LL * g.nTiles : raygenPaddedCount(g.cols + 1, g.count);
+    return g.tiles ? 32LL * *g.nTiles : raygenPaddedCount(g.cols + 1, g.count);
 }
 
 // Kept out of line so their FP64 normalisation / cube-map code does not raise the register count of the
@@ -527,7 +531,14 @@ __device__ __forceinline__ void walkRays(const bool ANY, const int GEN, const Sc
     int objN = -1, triN = -1;
     int obj = 0;                       // object loop position
     int cur = kDone, sp = 0;           // search-BVH cursor of the mesh being walked
+    // The node array of the mesh being walked stays in registers: reading it through the Mesh record put a dependent load in
+    // front of every node fetch.  The record itself is only needed at leaves and is looked up again there (RTB_HOIST_NODES=0:
+    // the old form, kept for A/B).
+#if RTB_HOIST_NODES
+    const float4* nodesP = nullptr;
+#else
     const Mesh* me = nullptr;
+#endif
     bool found = false;
     int slotBest = 0x7fffffff, triM = -1;
     float tM = FLT_MAX, uM = 0.f, vM = 0.f;
@@ -645,9 +656,18 @@ __device__ __forceinline__ void walkRays(const bool ANY, const int GEN, const Sc
                         if (ANY && ob.material == MAT_TRANSPARENT) {
                             obj++;
                         } else if (ob.type == OBJ_MESH) {
+#if RTB_HOIST_NODES
+                            const Mesh* me = &sc.meshes[ob.mesh];
+#else
                             me = &sc.meshes[ob.mesh];
+#endif
                             if (me->nNodes == 0 || me->nTris == 0) obj++;   // missing .obj / no usable face: nothing to hit
-                            else { cur = 0; sp = 0; found = false; slotBest = 0x7fffffff; tM = tNear; }
+                            else {
+                                cur = 0; sp = 0; found = false; slotBest = 0x7fffffff; tM = tNear;
+#if RTB_HOIST_NODES
+                                nodesP = me->bvhNodes;
+#endif
+                            }
                         } else {
                             float t = FLT_MAX;
                             const bool ok = (ob.type == OBJ_SPHERE) ? hitSphere(r, ob.pos, ob.r2, t) : hitPlane(r, ob.pos, ob.normal, t);
@@ -673,13 +693,20 @@ __device__ __forceinline__ void walkRays(const bool ANY, const int GEN, const Sc
                 const unsigned innerM = __ballot_sync(FULL, atInner), leafM = __ballot_sync(FULL, atLeaf);
                 const bool runInner = innerM != 0 && __popc(leafM) < kLeafBatch;
                 if (runInner && atInner) {
+#if RTB_HOIST_NODES
+                    const Mesh* me = STAGED ? &sc.meshes[sc.objects[obj].mesh] : nullptr;
+#endif
                     for (int step = 0; step < kInnerSteps && cur >= 0; ++step) {
                         float4 a, b, c, d;
                         if (STAGED && me == sb.mesh && cur < sb.nNodes) {
                             const unsigned na = sb.nodesAddr + (unsigned)cur * 64u;
                             a = ldsF4(na); b = ldsF4(na + 16); c = ldsF4(na + 32); d = ldsF4(na + 48);
                         } else {
+#if RTB_HOIST_NODES
+                            const float4* nd = nodesP + (size_t)cur * 4;
+#else
                             const float4* nd = me->bvhNodes + (size_t)cur * 4;
+#endif
                             a = __ldg(nd); b = __ldg(nd + 1); c = __ldg(nd + 2); d = __ldg(nd + 3);
                         }
                         if (STATS) acc.nNodes[ANY]++;
@@ -705,6 +732,9 @@ __device__ __forceinline__ void walkRays(const bool ANY, const int GEN, const Sc
                 } else if (!runInner && atLeaf) {
                     const int code = ~cur;
                     const int first = code >> 3, count = (code & 7) + 1;
+#if RTB_HOIST_NODES
+                    const Mesh* me = &sc.meshes[sc.objects[obj].mesh];
+#endif
                     const float4* tp = me->bvhTris + (size_t)first * 3;
                     const bool trisStaged = STAGED && me == sb.mesh && sb.nTris > 0;
                     unsigned ta = sb.trisAddr + (unsigned)first * 48u;
@@ -1135,13 +1165,102 @@ __global__ void k_fill_background(float* __restrict__ fb, int width, int height,
     }
 }
 
-// The 8x4 tiles inside the generation rectangle whose primary rays are NOT generated (outside the projected coverage of the
-// geometry, scene_pack.h primaryRect): their pixels are misses by construction -> background colour.  One warp per tile.
-__global__ void k_fill_tiles(float* __restrict__ fb, int width, const int* __restrict__ tiles, int nTiles, const int* __restrict__ rows, int nRows,
-    int x0, int cols, V3 bg)
+// ------------------------------------------------------------------------------------------------
+// screen coverage of the geometry -> the tiles primary rays are generated for (all on the device)
+// ------------------------------------------------------------------------------------------------
+// primaryRect (scene_pack.h, host) bounds the generation RECTANGLE with the root boxes.  Inside it most 8x4 tiles of a thin or
+// diagonal object are still empty (cfg4: 1.0 M of 1.6 M generated primaries missed everything).  With finer boxes — a mesh's
+// search-BVH child boxes 10 levels down, spheres' boxes — the same projection gives a per-row, per-8-pixel-cell COVERAGE bitmap;
+// tiles outside it are misses by construction and get the background colour instead of rays.  Everything runs on the device
+// (a camera sweep changes it every frame): k_cover_mark projects the boxes with the device copy of the camera, k_tile_lists
+// turns the bitmap into the list of tiles to generate rays for and the list of tiles to fill.  The lists stay resident while
+// camera and rows do not change.  tests/test_fast_path_cpu.py checks the same projection (scene_pack.h) against the oracle's
+// hit pixels; the frames stay bit-identical (goldens, camera sweeps, rotated cameras).
+struct CoverCtr {
+    int nKept, nSkipped;
+    int invalid;           // a box reaches behind the camera plane / is not finite: no finer bound, every tile is kept
+    int pad;
+    long long livePixels;  // pixels of the kept tiles (statistics)
+};
+
+// one warp per box: project its 8 corners like pixelBoundsOfBox (scene_pack.h), mark rows x cells of the expanded pixel rectangle
+__global__ void k_cover_mark(const Scene* __restrict__ scp, const float* __restrict__ boxes, int nBoxes, unsigned* __restrict__ bits, int cellsX, CoverCtr* ctr)
+{
+    const int lane = threadIdx.x & 31;
+    const int width = scp->width, height = scp->height;
+    const int wordsPerRow = (cellsX + 31) / 32;
+    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nBoxes; w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const float* b = boxes + (size_t)w * 6;
+        double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
+        bool ok = true;
+        for (int c = 0; c < 8; ++c) {
+            const double v0 = (double)b[(c & 1) ? 3 : 0] - scp->camPos.x, v1 = (double)b[(c & 2) ? 4 : 1] - scp->camPos.y, v2 = (double)b[(c & 4) ? 5 : 2] - scp->camPos.z;
+            if (!(isfinite(v0) && isfinite(v1) && isfinite(v2))) { ok = false; break; }
+            double cam[3];
+            for (int i = 0; i < 3; ++i) cam[i] = v0 * scp->camM[i * 4 + 0] + v1 * scp->camM[i * 4 + 1] + v2 * scp->camM[i * 4 + 2];
+            const double len = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+            if (!(cam[2] < -1e-4 * len)) { ok = false; break; }
+            const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
+            const double px = (xPix / ((double)scp->camScale * scp->camAspect) + 1.0) * width / 2.0 - 1.0;
+            const double py = (-yPix / (double)scp->camScale + 1.0) * height / 2.0 - 1.0;
+            if (!(isfinite(px) && isfinite(py))) { ok = false; break; }
+            minX = fmin(minX, px); maxX = fmax(maxX, px);
+            minY = fmin(minY, py); maxY = fmax(maxY, py);
+        }
+        if (!ok) { if (lane == 0) atomicExch(&ctr->invalid, 1); continue; }
+        const int wm1 = width - 1, hm1 = height - 1;
+        const int px0 = (int)fmax(0.0, fmin((double)wm1, floor(minX) - 2)), px1 = (int)fmax(0.0, fmin((double)wm1, ceil(maxX) + 3));
+        const int py0 = (int)fmax(0.0, fmin((double)hm1, floor(minY) - 2)), py1 = (int)fmax(0.0, fmin((double)hm1, ceil(maxY) + 3));
+        if (px1 <= px0 || py1 <= py0) continue;
+        const int c0 = px0 / 8, c1 = (px1 - 1) / 8;                       // cells [c0, c1]
+        const int w0 = c0 / 32, w1 = c1 / 32;
+        const int nWords = w1 - w0 + 1;
+        for (int i = lane; i < (py1 - py0) * nWords; i += 32) {
+            const int y = py0 + i / nWords, wd = w0 + i % nWords;
+            const int lo = max(c0, wd * 32) - wd * 32, hi = min(c1, wd * 32 + 31) - wd * 32;
+            const unsigned mask = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1)) & ~((1u << lo) - 1);
+            atomicOr(&bits[(size_t)y * wordsPerRow + wd], mask);
+        }
+    }
+}
+
+// one thread per 8x4 tile of the generation grid: covered (or no valid bitmap) -> kept list, else -> skipped list
+__global__ void k_tile_lists(const unsigned* __restrict__ bits, int cellsX, const int* __restrict__ rows, int nRows, int x0, int cols,
+    int* __restrict__ kept, int* __restrict__ skipped, CoverCtr* ctr)
+{
+    const int tilesX = (cols + 7) / 8, tilesY = (nRows + 3) / 4;
+    const int wordsPerRow = (cellsX + 31) / 32;
+    const bool all = ctr->invalid != 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ((tilesX * tilesY + 31) & ~31); t += gridDim.x * blockDim.x) {
+        bool valid = t < tilesX * tilesY, covered = false;
+        int live = 0;
+        if (valid) {
+            const int tx = t % tilesX, ty = t / tilesX;
+            const int xa = x0 + tx * 8, xb = min(xa + 7, x0 + cols - 1);
+            const int r0 = ty * 4, r1 = min(r0 + 4, nRows);
+            live = (r1 - r0) * (xb - xa + 1);
+            covered = all;
+            for (int rr = r0; rr < r1 && !covered; ++rr) {
+                const unsigned* rowBits = bits + (size_t)rows[rr] * wordsPerRow;
+                const int ca = xa / 8, cb = xb / 8;
+                covered = ((rowBits[ca / 32] >> (ca & 31)) & 1u) || ((rowBits[cb / 32] >> (cb & 31)) & 1u);
+            }
+        }
+        // warp-aggregated appends keep the lists in (nearly) raster order
+        const int k = warpAlloc(&ctr->nKept, valid && covered, 1);
+        const int s = warpAlloc(&ctr->nSkipped, valid && !covered, 1);
+        if (valid && covered) { kept[k] = t; atomicAdd((unsigned long long*)&ctr->livePixels, (unsigned long long)live); }
+        else if (valid) skipped[s] = t;
+    }
+}
+
+// The tiles of the skipped list: their pixels are misses by construction -> background colour.  One warp per tile.
+__global__ void k_fill_tiles(float* __restrict__ fb, int width, const int* __restrict__ tiles, const CoverCtr* __restrict__ ctr, const int* __restrict__ rows,
+    int nRows, int x0, int cols, V3 bg)
 {
     const int tilesX = (cols + 7) / 8;
     const int lane = threadIdx.x & 31;
+    const int nTiles = ctr->nSkipped;
     for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nTiles; w += ((long long)gridDim.x * blockDim.x) >> 5) {
         const int tile = tiles[w];
         const int xr = (tile % tilesX) * 8 + (lane & 7), rr = (tile / tilesX) * 4 + (lane >> 3);
