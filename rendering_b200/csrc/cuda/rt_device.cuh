@@ -9,9 +9,6 @@
 // The functions are __host__ __device__ so tests/ can also compile this header with g++ and check
 // the arithmetic on the CPU box (tests/shim); the product only ever calls them from kernels.
 #pragma once
-#ifndef RTB_SLAB_FMA
-#define RTB_SLAB_FMA 0
-#endif
 
 #include <stdint.h>
 #include <math.h>
@@ -209,9 +206,6 @@ RT_HD V3 cameraDir(const Scene& sc, float px, float py)
 struct RayCtx {   // ray plus the per-ray invariants intersectBox recomputes per call (objects.cpp:543-544)
     V3 o, d, inv;
     int sx, sy, sz;
-#if RTB_SLAB_FMA
-    V3 noi;       // -(o * inv): the culling test of the search BVH is one fused multiply-add per plane (slabEntry)
-#endif
 };
 RT_HD RayCtx makeRay(V3 o, V3 d)
 {
@@ -219,9 +213,6 @@ RT_HD RayCtx makeRay(V3 o, V3 d)
     r.o = o; r.d = d;
     r.inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     r.sx = r.inv.x < 0; r.sy = r.inv.y < 0; r.sz = r.inv.z < 0;
-#if RTB_SLAB_FMA
-    r.noi = mk(-(o.x * r.inv.x), -(o.y * r.inv.y), -(o.z * r.inv.z));
-#endif
     return r;
 }
 
@@ -695,20 +686,11 @@ RT_HD int eligibleSlot(const Scene& sc, const Mesh& me, const RayCtx& r, int tri
 
 // conservative ray-segment / padded-box test for CULLING only (never decides a hit): NaN-ignoring
 // min/max keep a NaN axis from rejecting
-// RTB_SLAB_FMA: plane distance = fma(plane, inv, -(o * inv)) instead of (plane - o) * inv.  The two differ by rounding only
-// (the boxes are padded by 1e-4 of the mesh diagonal, orders of magnitude more) and in how an axis-parallel ray degenerates:
-// inf - inf gives NaN where the subtract form gives +-inf, and a NaN axis never rejects — the test stays conservative.
 RT_HD float slabEntry(const RayCtx& r, float lox, float loy, float loz, float hix, float hiy, float hiz, float tFar, bool& hit)
 {
-#if RTB_SLAB_FMA
-    const float t0x = fmaf(lox, r.inv.x, r.noi.x), t1x = fmaf(hix, r.inv.x, r.noi.x);
-    const float t0y = fmaf(loy, r.inv.y, r.noi.y), t1y = fmaf(hiy, r.inv.y, r.noi.y);
-    const float t0z = fmaf(loz, r.inv.z, r.noi.z), t1z = fmaf(hiz, r.inv.z, r.noi.z);
-#else
     const float t0x = (lox - r.o.x) * r.inv.x, t1x = (hix - r.o.x) * r.inv.x;
     const float t0y = (loy - r.o.y) * r.inv.y, t1y = (hiy - r.o.y) * r.inv.y;
     const float t0z = (loz - r.o.z) * r.inv.z, t1z = (hiz - r.o.z) * r.inv.z;
-#endif
     const float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
     const float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tFar));
     hit = tn <= tf;

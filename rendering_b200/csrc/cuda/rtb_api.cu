@@ -460,8 +460,15 @@ void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk
     // small tiles keep the groups of an SM out of phase and the dynamic tile cursor balances the SMs.
     // Growing the tile when a rank of a multi-GPU frame has only 1-2 tiles per group (to save a "round") was measured too:
     // 1/4 of cfg4's rows 0.277 -> 0.317 ms, 1/8 0.267 -> 0.285 ms (tools/gpu_strips.py): kept at one batch per warp.
+    // A frame with fewer 256-ray tiles than HALF the resident groups (small images, short SSAA lists) gets 64-ray tiles:
+    // four times the groups share the work, and above all the few heavy tiles of a deep scene (the pixels of a glass sphere
+    // spawn two children per level) are cut in four.  Measured (256 / 128 / 64 / 32 rays, pass 1 + SSAA ms): cfg1 256x256
+    // depth 10 0.295+0.261 / 0.205+0.180 / 0.180+0.169 / 0.179+0.179; cfg2's SSAA list (142 tiles) 0.097 / 0.093 / 0.091 /
+    // 0.120.  With enough tiles to fill the machine small tiles only idle lanes: cfg4 0.408 / 0.473 / 0.644 / 1.002 ms,
+    // cfg3's SSAA list (344 tiles) 0.136 / 0.137 / 0.189 / 0.259.
     static const int forced = getenv("RTB_TILE_RAYS") ? atoi(getenv("RTB_TILE_RAYS")) : 0;
-    long long R = forced > 0 ? forced : rtk::kTileThreads;
+    const long long tiles256 = (total + rtk::kTileThreads - 1) / rtk::kTileThreads;
+    long long R = forced > 0 ? forced : (2 * tiles256 < groups ? 64 : rtk::kTileThreads);
     R = std::max<long long>(32, std::min(1024LL, R)) & ~31LL;
     const int S = h->scene.shadowRaysPerHit;
     h->tileCapRays = std::max<long long>(h->tileCapRays, deep ? 2 * R : R);
@@ -1185,14 +1192,18 @@ int rtb_set_camera(RtbHandle* h, const RtbCamera* camera)
 {
     if (!h || !camera) { g_err = "null argument"; return RTB_ERR_ARG; }
     return guarded([&]() {
-        h->scene.camPos = rtpack::v3of(camera->pos);
+        const rt::V3 pos = rtpack::v3of(camera->pos);
+        bool same = std::memcmp(&pos, &h->scene.camPos, sizeof pos) == 0 && std::memcmp(&camera->scale, &h->scene.camScale, sizeof(float)) == 0
+            && std::memcmp(&camera->aspect, &h->scene.camAspect, sizeof(float)) == 0;
+        for (int i = 0; i < 16; ++i) same = same && std::memcmp(&camera->rMatrix[i], &h->scene.camM[i], sizeof(float)) == 0;
+        h->scene.camPos = pos;
         for (int i = 0; i < 16; ++i) h->scene.camM[i] = camera->rMatrix[i];
         h->scene.camScale = camera->scale;
         h->scene.camAspect = camera->aspect;
         *h->scenePinned = h->scene;          // uploaded by the next render call on its own stream (uploadSceneHeader)
         h->sceneDirty = true;
         h->pendingH2D += sizeof(rt::Scene);
-        computePrimaryRect(h);
+        if (!same) computePrimaryRect(h);    // a camera that did not move keeps the rectangle and the resident tile lists
         return RTB_OK;
     });
 }
