@@ -78,6 +78,7 @@ struct QueueBufs {
 
 } // namespace
 
+constexpr long long kEarlyOutRatio = 16;   // early output pays while the re-traced pixels are fewer than 1/16 of the frame's
 enum OutputKind { OUT_FLOAT = 0, OUT_BGR8 = 1, OUT_SCATTER = 2 };   // OUT_SCATTER: rows go to their image position of a full-frame device buffer
 
 struct RtbHandle {
@@ -88,6 +89,11 @@ struct RtbHandle {
         std::vector<int> owned;
         void* fb = nullptr; float* pass1 = nullptr; int fbOnDevice = 0; OutputKind kind = OUT_FLOAT;
         bool pipelinedCopy = false;      // OUT_BGR8 to a host buffer through copyStream (rtb_render_bgr8_begin)
+        // early output: the pass-1 bytes leave for the host right after pass 1 (copy engine, beside Sobel and the SSAA pass), then
+        // only the re-traced pixels are rewritten in place through fbDev, the device-side address of the (pinned) host buffer
+        bool earlyOut = false;
+        void* fbDev = nullptr;
+        int earlyStage = 0;
         bool ssaa = false, literalWalk = false, culled = false;
         int genX0 = 0, genCols = 0, nGenRows = 0, nInitRows = 0;
         bool cover = false;                      // rays only for the 8x4 tiles of the resident kept list (k_tile_lists), the rest is filled
@@ -156,6 +162,7 @@ struct RtbHandle {
     DevBuf hitTuv, hitObj, surfP, surfN, surfC, vis, interiors, slots, flagged, rowsA, rowsB, rowsC, userRays, outStage, tilesKept, tilesSkipped;
     DevBuf ctrBuf;                     // FrameCtr followed by 2 passes x (levels + 1) LevelCtr
     void* hCtr = nullptr;              // pinned mirror of ctrBuf
+    void* hCtrDev = nullptr;           // ... and its device-side address: the counters come back by plain stores (k_store_words)
     size_t ctrBytes = 0;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     // pipelined output (rtb_render_bgr8_begin): the frame's bytes leave on a second stream from one of two staging buffers, so
@@ -347,11 +354,11 @@ struct KernelSpan {
         a = takeEvent(h); b = takeEvent(h);
         CK(cudaEventRecord(a, st));
     }
-    void done()
+    void done(int launches = 1)     // launches: kernels enqueued inside the span (every one is counted)
     {
         launchCheck();
-        h->stats.kernelLaunches++;
-        h->stats.launchesKernel[kind]++;
+        h->stats.kernelLaunches += launches;
+        h->stats.launchesKernel[kind] += launches;
         if (!h->kernelTiming) return;
         CK(cudaEventRecord(b, st));
         h->spans.push_back({ kind, a, b });
@@ -706,6 +713,7 @@ void enqueueAttempt(RtbHandle* h)
     }
     if (f.cover) {
         KernelSpan ks(h, st, RTB_K_RAYGEN);
+        const int coverLaunches = f.rebuildLists ? 3 : 1;
         if (f.rebuildLists) {
             const int cellsX = (w + 7) / 8;
             CK(cudaMemsetAsync(h->coverBits.p, 0, (size_t)ht * ((cellsX + 31) / 32) * sizeof(unsigned), st));
@@ -721,7 +729,7 @@ void enqueueAttempt(RtbHandle* h)
         }
         rtk::k_fill_tiles<<<gridFor(h, 32LL * f.tilesTotal), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->tilesSkipped.as<int>(), h->coverCtrDev,
             h->rowsA.as<int>(), f.nGenRows, f.genX0, f.genCols, sc.background);
-        ks.done();
+        ks.done(coverLaunches);
     }
     CK(cudaMemsetAsync(h->ctrBuf.p, 0, h->ctrBytes, st));
     if (f.n0 > 0) {
@@ -769,6 +777,22 @@ void enqueueAttempt(RtbHandle* h)
         if (!f.fbOnDevice) h->stats.d2hBytes += bytes;
     };
     if (f.pass1) emit(f.pass1, OUT_FLOAT, owned.size() * (size_t)w * 3 * sizeof(float));
+    if (f.earlyOut) {
+        const int k = h->pipeParity;
+        h->pipeParity ^= 1;
+        f.earlyStage = k;
+        h->pipeStage[k].reserve(f.outBytes, st, false);
+        CK(cudaStreamWaitEvent(st, h->pipeCopied[k], 0));
+        KernelSpan ks(h, st, RTB_K_OUTPUT);
+        rtk::k_quantize_bgr8<<<gridFor(h, (long long)(f.outBytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+            (int)owned.size(), h->pipeStage[k].as<unsigned int>());
+        ks.done();
+        CK(cudaEventRecord(h->pipeReady[k], st));
+        CK(cudaStreamWaitEvent(h->copyStream, h->pipeReady[k], 0));
+        CK(cudaMemcpyAsync(f.fb, h->pipeStage[k].p, f.outBytes, cudaMemcpyDeviceToHost, h->copyStream));
+        CK(cudaEventRecord(h->pipeCopied[k], h->copyStream));
+        h->stats.d2hBytes += f.outBytes;
+    }
 
     if (f.ssaa) {
         {
@@ -801,7 +825,15 @@ void enqueueAttempt(RtbHandle* h)
     } else {
         CK(cudaEventRecord(h->ev[2], st));
     }
-    if (f.pipelinedCopy && f.fb && !owned.empty()) {
+    if (f.earlyOut) {
+        // the pass-1 bytes have arrived (or are about to); rewrite what the SSAA pass changed
+        CK(cudaStreamWaitEvent(st, h->pipeCopied[f.earlyStage], 0));
+        KernelSpan ks(h, st, RTB_K_OUTPUT);
+        rtk::k_patch_bgr8<<<gridFor(h, std::max(1LL, h->flaggedSeen > 0 ? h->flaggedSeen : h->capFlagged)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w,
+            owned.front(), owned.back() + 1, h->flagged.as<int>(), (int)h->capFlagged, h->dFrame(), static_cast<unsigned int*>(f.fbDev),
+            (long long)(f.outBytes / 4));
+        ks.done();
+    } else if (f.pipelinedCopy && f.fb && !owned.empty()) {
         // bytes -> staging buffer k on the render stream; the copy to the host runs on copyStream behind an event, and the render
         // stream only waits for it again when buffer k is reused two frames later
         const int k = h->pipeParity;
@@ -822,7 +854,13 @@ void enqueueAttempt(RtbHandle* h)
     }
     CK(cudaEventRecord(h->ev[3], st));
     // the frame's counters, read back behind everything else (endRows waits for them)
-    CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
+    if (h->hCtrDev) {
+        KernelSpan ks(h, st, RTB_K_OUTPUT);
+        rtk::k_store_words<<<1, 256, 0, st>>>(h->ctrBuf.as<unsigned int>(), static_cast<unsigned int*>(h->hCtrDev), (int)(h->ctrBytes / 4));
+        ks.done();
+    } else {
+        CK(cudaMemcpyAsync(h->hCtr, h->ctrBuf.p, h->ctrBytes, cudaMemcpyDeviceToHost, st));
+    }
     h->stats.d2hBytes += h->ctrBytes;
 }
 
@@ -906,6 +944,24 @@ void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     f.flaggedCap = f.ssaa ? std::min(f.interiorPixels, std::max(f.interiorPixels / 16, h->flaggedSeen + h->flaggedSeen / 4 + 1024)) : 0;
     const size_t outRowBytes = kind == OUT_BGR8 ? (size_t)((w * 3 + 3) & ~3) : (size_t)w * 3 * sizeof(float);
     f.outBytes = owned.size() * outRowBytes;
+    // early output needs: bytes for a host buffer the device can address (pinned), an SSAA pass to hide the copy behind, one
+    // contiguous range of rows
+    // ... and few enough re-traced pixels: rewriting one costs about as much PCIe time as copying kEarlyOutRatio pixels' bytes
+    // (measured), so the last frame's count decides (RTB_EARLY_OUTPUT=0 / 1: never / always)
+    const char* earlyEnv = getenv("RTB_EARLY_OUTPUT");
+    const int earlyMode = earlyEnv ? atoi(earlyEnv) : -1;
+    const bool fewFlagged = h->flaggedSeen > 0 && h->flaggedSeen * kEarlyOutRatio < (long long)owned.size() * w;
+    // (a frame loop on the begin / end halves hides the copy behind the NEXT frame instead: pipelinedCopy)
+    if ((earlyMode == 1 || (earlyMode < 0 && fewFlagged && !pipelinedCopy)) && kind == OUT_BGR8 && !fbOnDevice && fb && f.ssaa && !f.literalWalk
+        && owned.back() - owned.front() + 1 == (int)owned.size()) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, fb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            f.earlyOut = true;
+            f.fbDev = attr.devicePointer;
+        } else {
+            cudaGetLastError();
+        }
+    }
     f.active = true;
     enqueueAttempt(h);
 }
@@ -1148,6 +1204,7 @@ int rtb_create(const RtbScene* s, int device, uint32_t createFlags, RtbHandle** 
         h->ctrBuf.reserve(h->ctrBytes, h->ownStream, false);
         CK(cudaMallocHost(&h->hCtr, h->ctrBytes));
         std::memset(h->hCtr, 0, h->ctrBytes);
+        if (cudaHostGetDevicePointer(&h->hCtrDev, h->hCtr, 0) != cudaSuccess) { h->hCtrDev = nullptr; cudaGetLastError(); }
         // one resident wave of the persistent traversal kernels with this scene's stack size
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[0], rtk::k_walk<false, rtk::GEN_QUEUE>, rtk::kBlock, stackBytes(h)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->walkBlocksPerSm[1], rtk::k_walk<false, rtk::GEN_PRIMARY>, rtk::kBlock, stackBytes(h)));

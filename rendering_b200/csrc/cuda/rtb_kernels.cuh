@@ -1390,6 +1390,23 @@ __global__ void k_scatter_rows(const float* __restrict__ fb, int width, const in
 // saveImage's pixel conversion on the device (util.cpp:46-56): rows bottom-up, B,G,R byte order, each channel
 // (uint8)(clamp(0,1,v)*255), rows padded to a multiple of 4 bytes.  Output row j holds image row rows[nRows-1-j].
 // One thread converts 4 bytes (= 4 channels) and stores them as one 32-bit word.
+__device__ __forceinline__ unsigned int bgrWord(const float* __restrict__ srcRow, int width, int wordInRow)
+{
+    unsigned int word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const int byteInRow = wordInRow * 4 + b;
+        unsigned int v = 0;
+        if (byteInRow < width * 3) {
+            const int px = byteInRow / 3, ch = 2 - (byteInRow - px * 3);   // B,G,R
+            const float c = clampf_(0.0f, 1.0f, srcRow[px * 3 + ch]);
+            v = (unsigned int)(unsigned char)(c * 255);
+        }
+        word |= v << (8 * b);
+    }
+    return word;
+}
+
 __global__ void k_quantize_bgr8(const float* __restrict__ fb, int width, const int* __restrict__ rows, int nRows, unsigned int* __restrict__ out)
 {
     const int rowBytes = (width * 3 + 3) & ~3;
@@ -1398,21 +1415,74 @@ __global__ void k_quantize_bgr8(const float* __restrict__ fb, int width, const i
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(i / rowWords);
         const int wordInRow = (int)(i - (long long)j * rowWords);
-        const float* src = fb + (long long)rows[nRows - 1 - j] * width * 3;
-        unsigned int word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int byteInRow = wordInRow * 4 + b;
-            unsigned int v = 0;
-            if (byteInRow < width * 3) {
-                const int px = byteInRow / 3, ch = 2 - (byteInRow - px * 3);   // B,G,R
-                const float c = clampf_(0.0f, 1.0f, src[px * 3 + ch]);
-                v = (unsigned int)(unsigned char)(c * 255);
-            }
-            word |= v << (8 * b);
-        }
-        out[i] = word;
+        out[i] = bgrWord(fb + (long long)rows[nRows - 1 - j] * width * 3, width, wordInRow);
     }
+}
+
+// Early output (rtb_api.cu enqueueAttempt): the pass-1 frame's bytes are already on their way to the host while Sobel and the
+// SSAA pass run; afterwards only the pixels SSAA re-traced differ.  They are rewritten straight into the host buffer (`out` is
+// the device-side address of pinned host memory: the stores cross PCIe as posted writes, whose cost is per transaction, not per
+// byte).  So the unit is the 32-byte sector: a warp takes 32 flagged pixels (neighbours in the list are neighbours in the image,
+// k_sobel), finds the distinct sectors their bytes fall in, and rewrites each sector whole — 8 lanes, one 32-bit word each,
+// recomputed from the float frame — as ONE coalesced store.  A sector shared with the next warp is written twice with the same
+// bytes.  Rows [y0, y1) of the image are the buffer's rows, bottom-up; outWords = words of the buffer.
+__global__ void k_patch_bgr8(const float* __restrict__ fb, int width, int y0, int y1, const int* __restrict__ flagged, int cap, const FrameCtr* __restrict__ ctr,
+    unsigned int* __restrict__ out, long long outWords)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int n = min(ctr->ssaaPixels, cap);
+    const int lane = threadIdx.x & 31;
+    const int rowWords = ((width * 3 + 3) & ~3) >> 2;
+    const int nChunks = (n + 31) / 32;
+    for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nChunks; chunk += (gridDim.x * blockDim.x) >> 5) {
+        const int i = chunk * 32 + lane;
+        long long s0 = -1, s1 = -1;                    // sectors (32 B = 8 words) holding the pixel's first / last byte
+        if (i < n) {
+            const int pix = flagged[i];
+            const int y = pix / width, x = pix - y * width;
+            if (y >= y0 && y < y1) {
+                const long long byte0 = (long long)(y1 - 1 - y) * rowWords * 4 + (long long)x * 3;
+                s0 = byte0 >> 5;
+                s1 = (byte0 + 2) >> 5;
+                if (s1 == s0) s1 = -1;
+            }
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const long long s = pass == 0 ? s0 : s1;
+            // one lane per distinct sector: the lowest lane of every group of equal values
+            const unsigned same = __match_any_sync(FULL, s);
+            const bool leader = s >= 0 && (__ffs(same) - 1) == lane;
+            unsigned todo = __ballot_sync(FULL, leader);
+            while (todo) {
+                // the next (up to) four sectors, eight lanes each
+                long long mine = -1;
+                unsigned rest = todo;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int src = rest ? __ffs(rest) - 1 : 0;
+                    const long long sg = __shfl_sync(FULL, s, src);
+                    if (rest && (lane >> 3) == g) mine = sg;
+                    rest &= rest - 1;
+                }
+                todo = rest;
+                if (mine >= 0) {
+                    const long long word = mine * 8 + (lane & 7);
+                    if (word < outWords) {
+                        const int j = (int)(word / rowWords), wordInRow = (int)(word - (long long)j * rowWords);
+                        out[word] = bgrWord(fb + (long long)(y1 - 1 - j) * width * 3, width, wordInRow);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// the frame's counters into their pinned host mirror by plain stores: no copy-engine operation at the end of a frame, which
+// would queue behind a frame-sized device-to-host copy in flight
+__global__ void k_store_words(const unsigned int* __restrict__ src, unsigned int* __restrict__ dst, int n)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
 } // namespace rtk

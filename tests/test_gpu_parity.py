@@ -148,7 +148,7 @@ def test_tile_pipeline_equals_frame_wide_pipeline(name):
     assert np.array_equal(fa.view(np.uint32), fb.view(np.uint32)) and np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
     for k in ("rays", "primaryRays", "secondaryRays", "shadowRays", "ssaaPixels", "shadowRaysSkipped", "levels", "backgroundPixels"):
         assert sa[k] == sb[k], (k, sa[k], sb[k])
-    assert sa["kernelLaunches"] < sb["kernelLaunches"] and sa["kernelLaunches"] <= 6
+    assert sa["kernelLaunches"] < sb["kernelLaunches"] and sa["kernelLaunches"] <= 9    # every launch counted, incl. the coverage kernels and the counter store
     # strips and a second frame on the same handle
     part, _ = a.render(7, min(31, sc.height))
     assert np.array_equal(part.view(np.uint32), fa[7:min(31, sc.height)].view(np.uint32))
@@ -513,6 +513,7 @@ def test_begin_end_halves_render_the_same_frame_without_waiting_in_between():
     # rtb_render_end waits.  Same bits as the synchronous call, one frame in flight per handle, errors are loud.
     sc = rb.Scene(text=MIXED_SCENE)
     r = rb.Renderer(sc)
+    r.render()                                          # the first frame of a handle also builds its resident tile lists
     host, hs = r.render()
     dev = torch.zeros((sc.height, sc.width, 3), dtype=torch.float32, device="cuda:0")
     marker = torch.zeros(1, device="cuda:0")
@@ -598,6 +599,46 @@ def test_pixel_byte_output_equals_quantised_float_frame():
         assert st["d2hBytes"] < fb.nbytes / 3
         part, _ = r.render_bgr8(10, 31)
         assert np.array_equal(part, want[h - 31: h - 10])
+
+
+def test_early_output_into_pinned_host_memory_gives_the_same_bytes(monkeypatch):
+    # A pinned (device-addressable) host buffer takes the early-output path of rtb_render_bgr8: the pass-1 bytes are copied while
+    # Sobel / SSAA run and the re-traced pixels are rewritten in place by k_patch_bgr8.  A pageable buffer takes the plain path
+    # (quantise + copy after the SSAA pass).  Same bytes either way: full frames, odd row padding, partial row ranges, begin / end.
+    import torch
+    monkeypatch.setenv("RTB_EARLY_OUTPUT", "1")      # always (by default the last frame's SSAA count decides whether it pays)
+    cases = [rb.Scene(text=MIXED_SCENE), rb.Scene(text=MIXED_SCENE.replace("width=96", "width=99"))]
+    if HAVE_ASSETS:
+        cases.append(load("cfg4_shotgun_1080", 480, 270))
+        cases.append(load("cfg3_reflective_refractive_1080", 320, 180))
+    for sc in cases:
+        r = rb.Renderer(sc)
+        w, h = sc.width, sc.height
+        row_bytes = (w * 3 + 3) & ~3
+        want, st0 = r.render_bgr8()                                   # numpy buffer: pageable
+        assert st0["ssaaPixels"] > 0
+        pinned = torch.zeros((h, row_bytes), dtype=torch.uint8).pin_memory()
+        for _ in range(2):                                            # both staging buffers
+            pinned.fill_(0x5a)
+            got, st1 = r.render_bgr8(out=pinned.numpy())
+            assert np.array_equal(got, want)
+            assert st1["rays"] == st0["rays"] and st1["ssaaPixels"] == st0["ssaaPixels"]
+        y0, y1 = h // 5, h - h // 3
+        part = torch.zeros((y1 - y0, row_bytes), dtype=torch.uint8).pin_memory()
+        got, _ = r.render_bgr8(y0, y1, out=part.numpy())
+        assert np.array_equal(got, want[h - y1: h - y0])
+        pinned.fill_(0)
+        r.render_bgr8_begin(pinned.numpy())
+        r.render_end()
+        r.output_sync()
+        assert np.array_equal(pinned.numpy(), want)
+        # and with the heuristic deciding (either path): the same bytes
+        monkeypatch.delenv("RTB_EARLY_OUTPUT")
+        pinned.fill_(0)
+        r.render_bgr8(out=pinned.numpy())
+        assert np.array_equal(pinned.numpy(), want)
+        monkeypatch.setenv("RTB_EARLY_OUTPUT", "1")
+        r.close()
 
 
 GLASS_HALL = """
