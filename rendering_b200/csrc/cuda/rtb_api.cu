@@ -781,15 +781,21 @@ void enqueueAttempt(RtbHandle* h)
         const int k = h->pipeParity;
         h->pipeParity ^= 1;
         f.earlyStage = k;
-        h->pipeStage[k].reserve(f.outBytes, st, false);
-        CK(cudaStreamWaitEvent(st, h->pipeCopied[k], 0));
-        KernelSpan ks(h, st, RTB_K_OUTPUT);
-        rtk::k_quantize_bgr8<<<gridFor(h, (long long)(f.outBytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
-            (int)owned.size(), h->pipeStage[k].as<unsigned int>());
-        ks.done();
+        const void* src = h->slots.as<float>() + (size_t)owned.front() * w * 3;     // float rows: straight out of the frame
+        if (f.kind == OUT_BGR8) {
+            h->pipeStage[k].reserve(f.outBytes, st, false);
+            CK(cudaStreamWaitEvent(st, h->pipeCopied[k], 0));
+            KernelSpan ks(h, st, RTB_K_OUTPUT);
+            rtk::k_quantize_bgr8<<<gridFor(h, (long long)(f.outBytes / 4)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, h->rowsB.as<int>(),
+                (int)owned.size(), h->pipeStage[k].as<unsigned int>());
+            ks.done();
+            src = h->pipeStage[k].p;
+        }
+        // (float rows are read by the copy engine while the SSAA pass rewrites some of them: whatever it catches of those pixels
+        // is rewritten below)
         CK(cudaEventRecord(h->pipeReady[k], st));
         CK(cudaStreamWaitEvent(h->copyStream, h->pipeReady[k], 0));
-        CK(cudaMemcpyAsync(f.fb, h->pipeStage[k].p, f.outBytes, cudaMemcpyDeviceToHost, h->copyStream));
+        CK(cudaMemcpyAsync(f.fb, src, f.outBytes, cudaMemcpyDeviceToHost, h->copyStream));
         CK(cudaEventRecord(h->pipeCopied[k], h->copyStream));
         h->stats.d2hBytes += f.outBytes;
     }
@@ -829,9 +835,13 @@ void enqueueAttempt(RtbHandle* h)
         // the pass-1 bytes have arrived (or are about to); rewrite what the SSAA pass changed
         CK(cudaStreamWaitEvent(st, h->pipeCopied[f.earlyStage], 0));
         KernelSpan ks(h, st, RTB_K_OUTPUT);
-        rtk::k_patch_bgr8<<<gridFor(h, std::max(1LL, h->flaggedSeen > 0 ? h->flaggedSeen : h->capFlagged)), rtk::kBlock, 0, st>>>(h->slots.as<float>(), w,
-            owned.front(), owned.back() + 1, h->flagged.as<int>(), (int)h->capFlagged, h->dFrame(), static_cast<unsigned int*>(f.fbDev),
-            (long long)(f.outBytes / 4));
+        const int grid = gridFor(h, std::max(1LL, h->flaggedSeen > 0 ? h->flaggedSeen : h->capFlagged));
+        if (f.kind == OUT_BGR8)
+            rtk::k_patch_rows<false><<<grid, rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, owned.front(), owned.back() + 1, h->flagged.as<int>(),
+                (int)h->capFlagged, h->dFrame(), static_cast<unsigned int*>(f.fbDev), (long long)(f.outBytes / 4));
+        else
+            rtk::k_patch_rows<true><<<grid, rtk::kBlock, 0, st>>>(h->slots.as<float>(), w, owned.front(), owned.back() + 1, h->flagged.as<int>(),
+                (int)h->capFlagged, h->dFrame(), static_cast<unsigned int*>(f.fbDev), (long long)(f.outBytes / 4));
         ks.done();
     } else if (f.pipelinedCopy && f.fb && !owned.empty()) {
         // bytes -> staging buffer k on the render stream; the copy to the host runs on copyStream behind an event, and the render
@@ -952,8 +962,8 @@ void beginRows(RtbHandle* h, const std::vector<int>& owned, void* fb, float* pas
     const int earlyMode = earlyEnv ? atoi(earlyEnv) : -1;
     const bool fewFlagged = h->flaggedSeen > 0 && h->flaggedSeen * kEarlyOutRatio < (long long)owned.size() * w;
     // (a frame loop on the begin / end halves hides the copy behind the NEXT frame instead: pipelinedCopy)
-    if ((earlyMode == 1 || (earlyMode < 0 && fewFlagged && !pipelinedCopy)) && kind == OUT_BGR8 && !fbOnDevice && fb && f.ssaa && !f.literalWalk
-        && owned.back() - owned.front() + 1 == (int)owned.size()) {
+    if ((earlyMode == 1 || (earlyMode < 0 && fewFlagged && !pipelinedCopy)) && (kind == OUT_BGR8 || kind == OUT_FLOAT) && !fbOnDevice && fb && f.ssaa
+        && !f.literalWalk && owned.back() - owned.front() + 1 == (int)owned.size()) {
         cudaPointerAttributes attr{};
         if (cudaPointerGetAttributes(&attr, fb) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
             f.earlyOut = true;

@@ -1426,7 +1426,10 @@ __global__ void k_quantize_bgr8(const float* __restrict__ fb, int width, const i
 // k_sobel), finds the distinct sectors their bytes fall in, and rewrites each sector whole — 8 lanes, one 32-bit word each,
 // recomputed from the float frame — as ONE coalesced store.  A sector shared with the next warp is written twice with the same
 // bytes.  Rows [y0, y1) of the image are the buffer's rows, bottom-up; outWords = words of the buffer.
-__global__ void k_patch_bgr8(const float* __restrict__ fb, int width, int y0, int y1, const int* __restrict__ flagged, int cap, const FrameCtr* __restrict__ ctr,
+// FLOATS = true: the same for the float32 frame (rtb_render into pinned host memory) — rows top-down, 12 bytes per pixel, and a
+// sector's words are the frame's own.
+template <bool FLOATS>
+__global__ void k_patch_rows(const float* __restrict__ fb, int width, int y0, int y1, const int* __restrict__ flagged, int cap, const FrameCtr* __restrict__ ctr,
     unsigned int* __restrict__ out, long long outWords)
 {
     const unsigned FULL = 0xffffffffu;
@@ -1441,9 +1444,9 @@ __global__ void k_patch_bgr8(const float* __restrict__ fb, int width, int y0, in
             const int pix = flagged[i];
             const int y = pix / width, x = pix - y * width;
             if (y >= y0 && y < y1) {
-                const long long byte0 = (long long)(y1 - 1 - y) * rowWords * 4 + (long long)x * 3;
+                const long long byte0 = FLOATS ? ((long long)(y - y0) * width + x) * 12 : (long long)(y1 - 1 - y) * rowWords * 4 + (long long)x * 3;
                 s0 = byte0 >> 5;
-                s1 = (byte0 + 2) >> 5;
+                s1 = (byte0 + (FLOATS ? 11 : 2)) >> 5;
                 if (s1 == s0) s1 = -1;
             }
         }
@@ -1469,8 +1472,12 @@ __global__ void k_patch_bgr8(const float* __restrict__ fb, int width, int y0, in
                 if (mine >= 0) {
                     const long long word = mine * 8 + (lane & 7);
                     if (word < outWords) {
-                        const int j = (int)(word / rowWords), wordInRow = (int)(word - (long long)j * rowWords);
-                        out[word] = bgrWord(fb + (long long)(y1 - 1 - j) * width * 3, width, wordInRow);
+                        if (FLOATS) {
+                            out[word] = __float_as_uint(fb[(long long)y0 * width * 3 + word]);
+                        } else {
+                            const int j = (int)(word / rowWords), wordInRow = (int)(word - (long long)j * rowWords);
+                            out[word] = bgrWord(fb + (long long)(y1 - 1 - j) * width * 3, width, wordInRow);
+                        }
                     }
                 }
             }

@@ -623,7 +623,15 @@ def test_early_output_into_pinned_host_memory_gives_the_same_bytes(monkeypatch):
             got, st1 = r.render_bgr8(out=pinned.numpy())
             assert np.array_equal(got, want)
             assert st1["rays"] == st0["rays"] and st1["ssaaPixels"] == st0["ssaaPixels"]
+        # the float frame takes the same route: rows copied early, re-traced pixels rewritten sector by sector
+        fwant, _ = r.render()
+        fpin = torch.full((h, w, 3), -1.0, dtype=torch.float32).pin_memory()
+        fgot, _ = r.render(out=fpin.numpy())
+        assert np.array_equal(fgot.view(np.uint32), fwant.view(np.uint32))
         y0, y1 = h // 5, h - h // 3
+        fpart = torch.full((y1 - y0, w, 3), -1.0, dtype=torch.float32).pin_memory()
+        fgot, _ = r.render(y0, y1, out=fpart.numpy())
+        assert np.array_equal(fgot.view(np.uint32), fwant[y0:y1].view(np.uint32))
         part = torch.zeros((y1 - y0, row_bytes), dtype=torch.uint8).pin_memory()
         got, _ = r.render_bgr8(y0, y1, out=part.numpy())
         assert np.array_equal(got, want[h - y1: h - y0])
