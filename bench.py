@@ -440,13 +440,13 @@ def ours(args):
                                  + ("NVLink stores into rank 0's double-buffered symmetric-memory frame + 1 device barrier" if exchange.transport == "p2p" else "1 NCCL gather"))
                    if world > 1 else "single GPU",
                    "timing": "CUDA events on the render stream per frame, summed; max over ranks",
-                   "pipeline": "tile (k_tile: whole recursion per 256-ray tile inside one persistent kernel per pass)"},
+                   "pipeline": "tile (k_tile: whole recursion per 256-ray tile inside one persistent kernel per pass; 64-ray tiles for passes that cannot fill the machine)"},
         "parity_sha_ok": parity["ok"] if parity else None, "parity": parity,
         "rays": {"reference_equivalent": rays, "note": "numerator of value / e2e: the reference's Render::trace call count for this frame (SURVEY.md 8d)",
                  "traced": traced, "background_prefilled_primaries": fst["backgroundPixels"] if world == 1 else None,
                  "dead_shadow_rays_not_traced": fst["shadowRaysSkipped"] if world == 1 else None,
                  "value_traced": traced / (ms_per_step * 1e-3) / 1e6 if traced else None},
-        "e2e": dict(head, what=("per frame: camera constants uploaded (rtb_set_camera), rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes), wall clock"
+        "e2e": dict(head, what=("per frame: camera constants uploaded (rtb_set_camera), rtb_render_bgr8 into a pinned host buffer (the call Scene::render() makes; BMP pixel bytes: copied to the host beside the Sobel / SSAA kernels, the re-traced pixels rewritten in place, DESIGN.md 4 'Early output'), wall clock"
                                 if world == 1 else f"per frame: camera uploaded on every rank, strips rendered, exchanged to rank 0 ({exchange.transport}), converted to BMP pixel bytes there and copied to pinned host memory; wall clock over all frames, no host barrier between frames")),
         "e2e_float": e2e["float"], "e2e_pipelined": e2e_pipe,
         "gpu_launches": launches, "launches_per_frame": launches / args.steps,

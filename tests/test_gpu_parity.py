@@ -704,6 +704,19 @@ def test_trace_and_cast_queries_vs_oracle():
         d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
         d[: n // 50, 0] = 0.0        # axis-parallel directions: 0 * inf = NaN inside the slab test (objects.cpp:543)
         d[n // 50: n // 25, 1] = 0.0
+        # ... and what the fused culling test of the search BVH (rt_device.cuh slabEntry: clamped inverse + slack) must survive:
+        # negative zeros, nearly axis-parallel directions (huge finite inverses, denormal inverses' reciprocals), two zero
+        # components, origins far from the scene
+        k = n // 25
+        d[k: k + 200, 0] = -0.0
+        d[k + 200: k + 400, 1] = np.float32(1e-20) * rng.choice([-1, 1], 200).astype(np.float32)
+        d[k + 400: k + 600, 0] = np.float32(3e-39)
+        d[k + 600: k + 800, 2] = rng.choice([-1, 1], 200).astype(np.float32) * np.float32(1e-12)
+        d[k + 800: k + 1000, :2] = 0.0
+        d[k + 800: k + 1000, 2] = -1.0
+        o[k + 1000: k + 1400] *= np.float32(400.0)
+        d[k + 1000: k + 1400] = -o[k + 1000: k + 1400] / np.linalg.norm(o[k + 1000: k + 1400], axis=1, keepdims=True).astype(np.float32) \
+            + rng.normal(size=(400, 3)).astype(np.float32) * np.float32(2e-3)      # aimed back at the scene
         rays = np.concatenate([o, d], 1)
         r = rb.Renderer(sc)
         tuv, ot = r.trace(rays)
