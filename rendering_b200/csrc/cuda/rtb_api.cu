@@ -467,7 +467,7 @@ void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk
     // small tiles keep the groups of an SM out of phase and the dynamic tile cursor balances the SMs.
     // Growing the tile when a rank of a multi-GPU frame has only 1-2 tiles per group (to save a "round") was measured too:
     // 1/4 of cfg4's rows 0.277 -> 0.317 ms, 1/8 0.267 -> 0.285 ms (tools/gpu_strips.py): kept at one batch per warp.
-    // A frame with fewer 256-ray tiles than HALF the resident groups (small images, short SSAA lists) gets 64-ray tiles:
+    // A pass with fewer 256-ray tiles than HALF the resident groups (small images, short SSAA lists) gets 64-ray tiles:
     // four times the groups share the work, and above all the few heavy tiles of a deep scene (the pixels of a glass sphere
     // spawn two children per level) are cut in four.  Measured (256 / 128 / 64 / 32 rays, pass 1 + SSAA ms): cfg1 256x256
     // depth 10 0.295+0.261 / 0.205+0.180 / 0.180+0.169 / 0.179+0.179; cfg2's SSAA list (142 tiles) 0.097 / 0.093 / 0.091 /
@@ -475,7 +475,10 @@ void enqueueTile(RtbHandle* h, cudaStream_t st, int pass, int genKind, const rtk
     // cfg3's SSAA list (344 tiles) 0.136 / 0.137 / 0.189 / 0.259.
     static const int forced = getenv("RTB_TILE_RAYS") ? atoi(getenv("RTB_TILE_RAYS")) : 0;
     const long long tiles256 = (total + rtk::kTileThreads - 1) / rtk::kTileThreads;
-    long long R = forced > 0 ? forced : (2 * tiles256 < groups ? 64 : rtk::kTileThreads);
+    // Where the tiles are uniform (no secondary rays) the cut only pays for really short passes: a rank's eighth of cfg4 (262
+    // tiles) is 10 % slower with 64-ray tiles on 8 GPUs (0.297 vs 0.267 ms per frame), hence the second condition.
+    const bool small = deep ? 2 * tiles256 < groups : 4 * tiles256 < groups;
+    long long R = forced > 0 ? forced : (small ? 64 : rtk::kTileThreads);
     R = std::max<long long>(32, std::min(1024LL, R)) & ~31LL;
     const int S = h->scene.shadowRaysPerHit;
     h->tileCapRays = std::max<long long>(h->tileCapRays, deep ? 2 * R : R);
