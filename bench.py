@@ -11,8 +11,11 @@ exactly (tests/test_gpu_parity.py), so both arms share the numerator.
 ours:       value  = rays / device time, scene and queues resident in HBM, framebuffer left in HBM,
                      CUDA events on the render stream, L2 flushed between timed frames.
             e2e    = the same frame through the public host-buffer call Scene::render() makes
-                     (rtb_render_bgr8 into pinned HOST memory: the frame arrives as the BMP's pixel
-                     bytes, D2H inside the call); e2e_float = rtb_render with a float32 host framebuffer.
+                     (rtb_set_camera + rtb_render_bgr8 into pinned HOST memory: the frame arrives as the BMP's pixel
+                     bytes, H2D and D2H inside the call — with a pinned buffer the bytes cross PCIe beside the Sobel /
+                     SSAA kernels and the re-traced pixels are rewritten in place); e2e_float = rtb_render with a float32
+                     host framebuffer; e2e_pipelined = the begin / end halves with two host buffers in turn.
+            gpu_launches = every kernel launched inside the timed region (RtbStats.kernelLaunches).
             roofline = the dominant kernel (k_tile, pass 1): frac = PHYSICAL DRAM bytes per launch (ncu capture at
                      HEAD, profiles/traffic.json) over its live CUDA-event time (handle created with
                      RTB_CREATE_KERNEL_TIMING) against the measured HBM peak; roofline.issue = the issue-slot
