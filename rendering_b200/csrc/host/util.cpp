@@ -6,6 +6,8 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <thread>
+#include <vector>
 
 #include "../../../include/rtb.h"
 
@@ -81,7 +83,16 @@ void loadBMP(const std::string& filename, std::vector<uint8_t>& rgb, int& width,
     const size_t got = fread(rgb.data(), 1, rgb.size(), f);   // a short file leaves zeros, as the
     (void)got;                                                // reference's unchecked fread would
     fclose(f);
-    for (size_t i = 0; i + 2 < rgb.size(); i += 3) std::swap(rgb[i], rgb[i + 2]);
+    // B,G,R -> R,G,B (util.cpp:100-106).  A 4096x4096 map is 16.7 M texels: the swap is split over a few threads (the three maps of
+    // shotgun.scene were 135 of the 180 ms the scene takes to load)
+    const size_t texels = rgb.size() / 3;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nThreads = texels >= (1u << 20) ? std::max<size_t>(1, std::min<size_t>(8, hw ? hw : 1)) : 1;
+    auto swapRange = [&rgb](size_t a, size_t b) { for (size_t t = a; t < b; ++t) std::swap(rgb[3 * t], rgb[3 * t + 2]); };
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < nThreads; ++k) pool.emplace_back(swapRange, texels * k / nThreads, texels * (k + 1) / nThreads);
+    swapRange(0, texels / nThreads);
+    for (std::thread& t : pool) t.join();
 }
 
 namespace {
