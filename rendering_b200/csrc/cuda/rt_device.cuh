@@ -472,6 +472,31 @@ RT_HD float fresnel(V3 dir, V3 n, float ior)   // scene.cpp:698-722
     return (rs * rs + rp * rp) / 2;
 }
 
+// Pixel bounds of the projection of a world-space box (lo.xyz, hi.xyz): the inverse of cameraDir for the box's 8 corners, in
+// double.  false when a corner is not finite or at / behind the camera plane (no bound).  One definition for the host's
+// rectangle (scene_pack.h primaryRect), the device's coverage bitmap (k_cover_mark) and the CPU tests of both.
+RT_HD bool pixelBoundsOfBox(const Scene& sc, const float* b, double& minX, double& maxX, double& minY, double& maxY)
+{
+    minX = 1e300; maxX = -1e300; minY = 1e300; maxY = -1e300;
+    for (int c = 0; c < 8; ++c) {
+        const double v0 = (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, v1 = (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, v2 = (double)b[(c & 4) ? 5 : 2] - sc.camPos.z;
+        if (!(isfinite(v0) && isfinite(v1) && isfinite(v2))) return false;
+        // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
+        double cam[3];
+        for (int i = 0; i < 3; ++i) cam[i] = v0 * sc.camM[i * 4 + 0] + v1 * sc.camM[i * 4 + 1] + v2 * sc.camM[i * 4 + 2];
+        const double len = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+        if (!(cam[2] < -1e-4 * len)) return false;                   // at or behind the camera plane: no bound
+        const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
+        // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
+        const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
+        const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
+        if (!(isfinite(px) && isfinite(py))) return false;
+        minX = fmin(minX, px); maxX = fmax(maxX, px);
+        minY = fmin(minY, py); maxY = fmax(maxY, py);
+    }
+    return true;
+}
+
 #if defined(__CUDA_ARCH__)
 #define RT_LDG(p) __ldg(p)
 #else

@@ -1183,30 +1183,15 @@ struct CoverCtr {
     long long livePixels;  // pixels of the kept tiles (statistics)
 };
 
-// one warp per box: project its 8 corners like pixelBoundsOfBox (scene_pack.h), mark rows x cells of the expanded pixel rectangle
+// one warp per box: project its 8 corners (rt_device.cuh pixelBoundsOfBox), mark rows x cells of the expanded pixel rectangle
 __global__ void k_cover_mark(const Scene* __restrict__ scp, const float* __restrict__ boxes, int nBoxes, unsigned* __restrict__ bits, int cellsX, CoverCtr* ctr)
 {
     const int lane = threadIdx.x & 31;
     const int width = scp->width, height = scp->height;
     const int wordsPerRow = (cellsX + 31) / 32;
     for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nBoxes; w += ((long long)gridDim.x * blockDim.x) >> 5) {
-        const float* b = boxes + (size_t)w * 6;
-        double minX = 1e300, maxX = -1e300, minY = 1e300, maxY = -1e300;
-        bool ok = true;
-        for (int c = 0; c < 8; ++c) {
-            const double v0 = (double)b[(c & 1) ? 3 : 0] - scp->camPos.x, v1 = (double)b[(c & 2) ? 4 : 1] - scp->camPos.y, v2 = (double)b[(c & 4) ? 5 : 2] - scp->camPos.z;
-            if (!(isfinite(v0) && isfinite(v1) && isfinite(v2))) { ok = false; break; }
-            double cam[3];
-            for (int i = 0; i < 3; ++i) cam[i] = v0 * scp->camM[i * 4 + 0] + v1 * scp->camM[i * 4 + 1] + v2 * scp->camM[i * 4 + 2];
-            const double len = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-            if (!(cam[2] < -1e-4 * len)) { ok = false; break; }
-            const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
-            const double px = (xPix / ((double)scp->camScale * scp->camAspect) + 1.0) * width / 2.0 - 1.0;
-            const double py = (-yPix / (double)scp->camScale + 1.0) * height / 2.0 - 1.0;
-            if (!(isfinite(px) && isfinite(py))) { ok = false; break; }
-            minX = fmin(minX, px); maxX = fmax(maxX, px);
-            minY = fmin(minY, py); maxY = fmax(maxY, py);
-        }
+        double minX, maxX, minY, maxY;
+        const bool ok = pixelBoundsOfBox(*scp, boxes + (size_t)w * 6, minX, maxX, minY, maxY);
         if (!ok) { if (lane == 0) atomicExch(&ctr->invalid, 1); continue; }
         const int wm1 = width - 1, hm1 = height - 1;
         const int px0 = (int)fmax(0.0, fmin((double)wm1, floor(minX) - 2)), px1 = (int)fmax(0.0, fmin((double)wm1, ceil(maxX) + 3));

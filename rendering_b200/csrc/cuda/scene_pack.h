@@ -175,24 +175,7 @@ inline void packFastPath(const RtbMesh& m, FastPath& out, bool buildSearch = tru
 // primary rays of every 8x4 tile outside it are misses by construction and are not generated at all.
 inline bool pixelBoundsOfBox(const rt::Scene& sc, const std::array<float, 6>& b, double& minX, double& maxX, double& minY, double& maxY)
 {
-    minX = 1e300; maxX = -1e300; minY = 1e300; maxY = -1e300;
-    for (int c = 0; c < 8; ++c) {
-        const double v[3] = { (double)b[(c & 1) ? 3 : 0] - sc.camPos.x, (double)b[(c & 2) ? 4 : 1] - sc.camPos.y, (double)b[(c & 4) ? 5 : 2] - sc.camPos.z };
-        if (!(std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]))) return false;
-        // world direction = camera direction (row vector) x rMatrix  =>  camera = world x rMatrix^T
-        double cam[3];
-        for (int i = 0; i < 3; ++i) cam[i] = v[0] * sc.camM[i * 4 + 0] + v[1] * sc.camM[i * 4 + 1] + v[2] * sc.camM[i * 4 + 2];
-        const double len = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-        if (!(cam[2] < -1e-4 * len)) return false;                   // at or behind the camera plane: no bound
-        const double xPix = cam[0] / -cam[2], yPix = cam[1] / -cam[2];
-        // renderWorker (scene.cpp:453-461): xPix = (2 (x + 1.0) / W - 1) scale aspect, yPix = -(2 (y + 1.0) / H - 1) scale
-        const double px = (xPix / ((double)sc.camScale * sc.camAspect) + 1.0) * sc.width / 2.0 - 1.0;
-        const double py = (-yPix / (double)sc.camScale + 1.0) * sc.height / 2.0 - 1.0;
-        if (!(std::isfinite(px) && std::isfinite(py))) return false;
-        minX = std::min(minX, px); maxX = std::max(maxX, px);
-        minY = std::min(minY, py); maxY = std::max(maxY, py);
-    }
-    return true;
+    return rt::pixelBoundsOfBox(sc, b.data(), minX, maxX, minY, maxY);      // rt_device.cuh: shared with the device's k_cover_mark
 }
 
 inline void primaryRect(const rt::Scene& sc, const std::vector<std::array<float, 6>>& bounds, bool unbounded, int r[4],
