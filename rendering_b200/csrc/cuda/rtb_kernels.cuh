@@ -2,7 +2,10 @@
 //
 // The reference renders one pixel at a time with a recursive castRay (scene.cpp:758-946).  Here a
 // frame is a sequence of breadth-first LEVELS (level = recursion depth); each level runs as
-// separate kernels over compacted queues:
+// separate STAGES over compacted queues.  The stage bodies below (walkRays, surfaceStage, shadeStage, combineStage) are
+// used twice: by the default tile pipeline (rtb_tile.cuh: k_tile runs all stages of a 256-ray tile inside one persistent
+// kernel per pass) and by the frame-wide kernels of this file, one launch per stage and level (RTB_CREATE_WAVEFRONT, the
+// literal-walk / counting handles):
 //
 //   k_walk<false, GEN>      closest hit over all objects (Render::trace + the search BVH); generates the primary
 //                           and SSAA rays itself (renderWorker, SSAAworker) and resolves their misses
@@ -14,8 +17,13 @@
 //                           reference's exact expression order (:858-890, :896-940)
 //   k_sobel                 edge mask + compaction of flagged pixels   (launchSSAA :554-568)
 //   k_ssaa_resolve          mean of the 4 re-traced samples            (SSAAworker :525-536)
-//   k_fill_background, k_gather_rows / k_scatter_rows / k_quantize_bgr8, k_count_ac / k_ac_resolve, k_rgb_to_rgba
-//                           frame pre-fill, output stages (incl. saveImage's conversion), showAC view, texture upload
+//   k_fill_background, k_cover_mark / k_tile_lists / k_fill_tiles
+//                           frame pre-fill; projected coverage of the geometry -> the 8x4 tiles primary rays are generated for
+//   k_gather_rows / k_scatter_rows / k_quantize_bgr8, k_patch_rows, k_store_words
+//                           output stages (incl. saveImage's conversion), early output's rewrite of the re-traced pixels in
+//                           a pinned host buffer, the frame's counters into their host mirror
+//   k_count_ac / k_ac_resolve, k_rgb_to_rgba
+//                           showAC view, texture upload
 //   k_raygen, k_ssaa_gen, k_trace, k_shadow
 //                           the LITERAL reference walk (objects.cpp:587-631) over materialised queues: parity of the
 //                           reference's work counters (RTB_CREATE_COUNTERS / RTB_CREATE_EXACT_WALK), not the timed path
